@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the DESMO fused train step (BASELINE.json metric: train iters/s + HBM GB/s of the fused residual+grad pass).
+
+  python bench.py --gpus N --steps K --warmup W            # this framework, N GPUs of one node (torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle/torch_port.py) on the host cores
+
+Workload (config.workload): "aneurysm-scale" -- n = 3 * 2^20 mesh points per GPU x m = 1000 snapshots, r = 4, polyorder = 2
+(K = 27 library terms), fp32, synthetic pulsatile data generated on the device (12.6 GB per GPU, >> L2), POD init on the
+device.  Weak scaling: every rank owns an equally sized slab of points; only the (K*m + 29)-float `red` buffer is all-reduced.
+One step = build_w + fused residual/grad pass + partial reduction + (all-reduce) + regulariser/Adamax update.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (points per GPU, m, r, polyorder, nF)
+    "aneurysm-scale": (3 * 2 ** 20, 1000, 4, 2, 0),
+    "aneurysm-script": (27000, 1000, 4, 2, 0),
+    "cylinder-script": (3961, 1001, 4, 3, 0),
+    "cylinder-fourier": (3961, 1001, 2, 2, 10),
+    "channel-script": (16384, 1000, 4, 2, 0),
+}
+METRIC = "train_iters_per_s"
+UNIT = "it/s"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+def synth_on_device(torch, n, m, dev, seed, x_offset=0, n_global=None):
+    """Pulsatile aneurysm-like data, generated on the device straight into the padded time-major layout:
+    8 smooth spatial fields x 5 temporal harmonics + noise, temporal mean removed (CYL:136-149), scaled by 1/sqrt(m) (ANEU:143)."""
+    ld = (n + 255) // 256 * 256
+    n_global = n_global or n
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    U = torch.zeros(m, ld, dtype=torch.float32, device=dev)
+    x = (torch.arange(n, device=dev, dtype=torch.float64) + x_offset) / max(n_global - 1, 1)
+    t = torch.arange(m, device=dev, dtype=torch.float64)
+    for q in range(8):
+        c = torch.randn(4, generator=g, dtype=torch.float64)
+        ph = torch.rand(4, generator=g, dtype=torch.float64) * 3.141592653589793
+        gq = sum(c[j] * torch.sin(3.141592653589793 * (j + 1) * (q + 1) * x + ph[j]) / (j + 1) for j in range(4))
+        a = torch.randn(6, generator=g, dtype=torch.float64)
+        psi = torch.rand(6, generator=g, dtype=torch.float64) * 6.283185307179586
+        aq = a[0] * 0 + sum(a[h] / h * torch.cos(6.283185307179586 * h * t / m + psi[h]) for h in range(1, 6))
+        U[:, :n].add_((aq[:, None] * gq[None, :]).to(torch.float32) / (q + 1))
+    gen = torch.Generator(device=dev).manual_seed(seed + 17 + x_offset % 9973)
+    chunk = 64
+    for t0 in range(0, m, chunk):
+        U[t0:t0 + chunk, :n].add_(0.02 * torch.randn(min(chunk, m - t0), n, device=dev, generator=gen))
+    U[:, :n].sub_(U[:, :n].mean(dim=0, keepdim=True))
+    U.mul_(1.0 / m ** 0.5)
+    return U
+
+
+def cpu_reference_leg(n_full, m, r, p, nF, steps, warmup, sample_points=None):
+    """The reference's CPU implementation of the step (oracle/torch_port.py) on a bounded slab of the same workload."""
+    import numpy as np
+    import torch
+
+    from oracle import desmo_oracle as orc
+    from oracle.torch_port import time_steps
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ns = min(n_full, sample_points or 2 ** 14)
+    X = orc.synthetic_snapshots("aneurysm", ns, m, seed=2)
+    modes, _, _, _ = orc.pod_analysis(X, r)
+    prm = orc.init_params(ns, m, p, r, nF=nF or None)
+    sec, _ = time_steps(prm, modes, np.ascontiguousarray(X.T), steps, warmup)
+    its_sample = 1.0 / sec
+    # per-step cost is linear in the number of points (every op is O(n*m*K)); scale the slab rate to the full workload
+    return {"value": its_sample * ns / n_full, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{ns} of {n_full} points x {m} snapshots, {steps} steps after {warmup} warm-up, torch CPU fp32 "
+                      f"{torch.get_num_threads()} threads, incl. the per-epoch fp64->fp32 re-collation (CYL:707-708); "
+                      f"{its_sample:.3f} it/s on the slab, scaled by {ns}/{n_full}"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="desmo_b200", choices=["desmo_b200", "reference"])
+    ap.add_argument("--workload", default="aneurysm-scale", choices=sorted(WORKLOADS))
+    ap.add_argument("--points", type=int, default=0, help="override points per GPU")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 fp32 FFMA, 2 tcgen05")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    n, m, r, p, nF = WORKLOADS[args.workload]
+    if args.points:
+        n = args.points
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = {"workload": f"{args.workload}: {n} points/GPU x {m} snapshots, r={r}, polyorder={p}" + (f", nF={nF}" if nF else "") +
+           ", fp32, point-sharded", "points_per_gpu": n, "snapshots": m, "r": r, "polyorder": p,
+           "cache": "inputs larger than L2 (12.6 GB/GPU streamed per step)" if n * m * 4 > 4e8 else "L2 flushed between steps"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        leg = cpu_reference_leg(n * world, m, r, p, nF, max(args.steps // 4, 3), 1, args.cpu_sample or None)
+        line = {"impl": "reference", "metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1000.0 / leg["value"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "cpu_baseline": leg,
+                "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (desmo_b200 has no CPU fallback)")
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from desmo_b200 import DESMO, DesmoTrainer, _lib
+
+    n_global = n * world
+    model = DESMO(n, m, p, r, 10000, device=dev, n_global=n_global, path=args.path)
+    e = model.engine
+    e.U = synth_on_device(torch, n, m, dev, seed=2, x_offset=rank * n, n_global=n_global)
+    sigma = e.pod_from_snapshot()  # POD init on the device (method of snapshots)
+    torch.cuda.synchronize()
+    trainer = DesmoTrainer(model, sched_every=10 ** 9, use_cuda_graph=True)  # no host sync inside the timed region
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    l2_flush = None if n * m * 4 > 4e8 else torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev)
+    for _ in range(args.warmup):
+        trainer.step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        if l2_flush is None:
+            ev0.record()
+            for _ in range(args.steps):
+                trainer.step()
+            ev1.record()
+            barrier()
+            ms_total = ev0.elapsed_time(ev1)
+        else:
+            ms_total = 0.0
+            for _ in range(args.steps):
+                l2_flush.fill_(1)
+                ev0.record()
+                trainer.step()
+                ev1.record()
+                torch.cuda.synchronize()
+                ms_total += ev0.elapsed_time(ev1)
+            barrier()
+        # dominant kernel alone: average launch duration of the fused residual+grad pass on its launching stream
+        e.build_w(False)
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kms = 0.0
+        for _ in range(args.steps):
+            if l2_flush is not None:
+                l2_flush.fill_(1)
+            k0.record()
+            e.fused_residual_grad()
+            k1.record()
+            torch.cuda.synchronize()
+            kms += k0.elapsed_time(k1)
+        kms /= args.steps
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    losses = [float(v) for v in e.losses.tolist()]
+
+    # ---- e2e: the reference-facing C-ABI call with HOST buffers (H2D of the batch + step + D2H of the losses per step) ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            lib = _lib.load()
+            host = torch.empty(m, n, dtype=torch.float32, pin_memory=True)
+            host.copy_(e.U[:, :n])
+            ss = ctypes.c_void_p()
+            _lib.check(lib.desmo_session_create(n, m, r, p, nF, args.path, ctypes.byref(ss)), "session_create")
+            import numpy as np
+
+            pod = np.ascontiguousarray(e.P[:, :n].t().double().cpu().numpy())
+            K = e.K
+            phi0 = np.ones((r, n), np.float32); gates0 = np.ones(K, np.float32); rows0 = np.ones((K, m), np.float32)
+            om0 = np.full(3 * r, 1e4, np.float32); lrs = np.array([1e-2, 1e-3, 1e-2, 1e3, 1e-2], np.float32)
+            cp = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+            _lib.check(lib.desmo_session_set_pod_host(ss, cp(pod)), "set_pod")
+            _lib.check(lib.desmo_session_set_params_host(ss, cp(phi0), cp(gates0), cp(rows0), None, cp(om0)), "set_params")
+            _lib.check(lib.desmo_session_set_hyper(ss, cp(lrs), 1e-3, 1e-4), "set_hyper")
+            lo = np.zeros(4, np.float32)
+            e_steps = max(2, min(args.steps, 5))
+            _lib.check(lib.desmo_session_step_host(ss, ctypes.c_void_p(host.data_ptr()), cp(lo)), "step_host")  # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                _lib.check(lib.desmo_session_step_host(ss, ctypes.c_void_p(host.data_ptr()), cp(lo)), "step_host")
+            torch.cuda.synchronize()
+            dt = torch.tensor([(time.perf_counter() - t0) / e_steps], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            lib.desmo_session_destroy(ss)
+            e2e = {"value": 1.0 / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(n * m * 4), "d2h_bytes_per_step": 16,
+                   "steps": e_steps, "call": "desmo_session_step_host (pinned host batch -> device, fused step, losses -> host)"}
+            del host
+        except Exception as ex:  # keep the device-resident number even if the host leg cannot run (e.g. pinned alloc)
+            e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        alg_bytes = 4.0 * n * m + 12.0 * n * r + 8.0 * e.K * m  # U once; phi, P in, dphi out; W in, E out
+        achieved = alg_bytes / (kms * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": world / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": cfg,
+                "global_iters_per_s": 1.0 / (ms_step * 1e-3),
+                "snapshot_gbs": world * 4.0 * n * m / (ms_step * 1e-3) / 1e9,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "kernel": "fused_residual_grad", "kernel_ms": kms, "peak_source": peak_src,
+                             "algorithmic_bytes": alg_bytes},
+                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": 4 * args.steps,
+                "losses_last_step": losses, "pod_sigma": [float(v) for v in sigma.tolist()],
+                "path": "tcgen05" if False else ("auto" if args.path == 0 else ("fp32" if args.path == 1 else "tcgen05"))}
+        if not args.no_cpu and world == 1:
+            try:
+                line["cpu_baseline"] = cpu_reference_leg(n, m, r, p, nF, 5, 1, args.cpu_sample or None)
+            except Exception as ex:
+                line["cpu_baseline"] = {"value": None, "error": str(ex)[:200]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,103 @@
+"""ctypes binding of libdesmo_b200.so (include/desmo_b200.h).  No fallback: a missing library or a failing call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from typing import Dict, List
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdesmo_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "desmo_b200.h")
+
+PATH_AUTO, PATH_FP32, PATH_TC = 0, 1, 2
+HYP_LR_GATES, HYP_LR_PHI, HYP_LR_Z, HYP_LR_OMEGA, HYP_LR_PERIOD, HYP_BETA, HYP_L1_LAMBDA, HYP_COUNT = range(8)
+MAX_R, MAX_P, MAX_K = 8, 7, 64
+
+
+class DesmoError(RuntimeError):
+    pass
+
+
+class Shape(C.Structure):
+    _fields_ = [("n", C.c_int64), ("ld", C.c_int64), ("n_global", C.c_int64), ("m", C.c_int32), ("mld", C.c_int32),
+                ("r", C.c_int32), ("polyorder", C.c_int32), ("nF", C.c_int32), ("path", C.c_int32)]
+
+
+_vp, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+_SP = C.POINTER(Shape)
+
+# name -> (restype, argtypes); must list every function declared in include/desmo_b200.h (tests check this)
+SIGNATURES: Dict[str, tuple] = {
+    "desmo_last_error": (C.c_char_p, []),
+    "desmo_version": (C.c_char_p, []),
+    "desmo_num_terms": (_i32, [_i32, _i32]),
+    "desmo_padded_k": (_i32, [_i32, _i32]),
+    "desmo_red_count": (_i64, [_SP]),
+    "desmo_workspace_bytes": (C.c_int, [_SP, C.POINTER(C.c_size_t)]),
+    "desmo_build_w": (C.c_int, [_SP] + [_vp] * 8),
+    "desmo_fused_residual_grad": (C.c_int, [_SP] + [_vp] * 9),
+    "desmo_adamax_update": (C.c_int, [_SP] + [_vp] * 26),
+    "desmo_assemble_grads": (C.c_int, [_SP] + [_vp] * 17),
+    "desmo_reconstruct": (C.c_int, [_SP] + [_vp] * 6),
+    "desmo_library_colnorm2": (C.c_int, [_SP] + [_vp] * 5),
+    "desmo_pod_gram": (C.c_int, [_SP] + [_vp] * 4),
+    "desmo_pod_eig": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "desmo_pod_project": (C.c_int, [_SP] + [_vp] * 5),
+    "desmo_session_create": (C.c_int, [_i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
+    "desmo_session_destroy": (C.c_int, [_vp]),
+    "desmo_session_set_pod_host": (C.c_int, [_vp, _vp]),
+    "desmo_session_set_params_host": (C.c_int, [_vp] * 6),
+    "desmo_session_set_hyper": (C.c_int, [_vp, _vp, _f, _f]),
+    "desmo_session_upload_snapshot_host": (C.c_int, [_vp, _vp]),
+    "desmo_session_step_host": (C.c_int, [_vp, _vp, _vp]),
+    "desmo_session_get_params_host": (C.c_int, [_vp] * 6),
+    "desmo_train_host": (C.c_int, [_i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i32, _vp, _i32]),
+}
+
+_lib = None
+
+
+def declared_symbols() -> List[str]:
+    """Function names declared in include/desmo_b200.h."""
+    src = open(HEADER_PATH).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(desmo_[a-z0-9_]+)\s*\(", src)))
+
+
+def load(build_if_missing: bool = True):
+    """Loads the shared library; builds it in-tree with nvcc when absent.  Raises DesmoError if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise DesmoError(f"{LIB_PATH} is missing and there is no CPU fallback; run `python -m desmo_b200.build`")
+        from . import build as _build
+
+        _build.build()
+    try:
+        lib = C.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise DesmoError(f"cannot load {LIB_PATH}: {e} (no CPU fallback)") from e
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().desmo_last_error().decode(errors="replace")
+        raise DesmoError(f"{what or 'desmo_b200'} failed (code {rc}): {msg}")
+
+
+def round_up(v: int, a: int) -> int:
+    return (v + a - 1) // a * a
+
+
+def make_shape(n: int, m: int, r: int, polyorder: int, nF: int = 0, n_global: int | None = None, path: int = PATH_AUTO,
+               ld: int | None = None, mld: int | None = None) -> Shape:
+    return Shape(n=n, ld=ld or round_up(n, 256), n_global=n_global or n, m=m, mld=mld or round_up(m, 16), r=r,
+                 polyorder=polyorder, nF=nF or 0, path=path)

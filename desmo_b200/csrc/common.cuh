@@ -1,0 +1,156 @@
+// Shared definitions for the desmo_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/desmo_b200.h"
+
+namespace desmo {
+
+constexpr int kMaxR = DESMO_MAX_R;
+constexpr int kMaxP = DESMO_MAX_P;
+constexpr int kMaxK = DESMO_MAX_K;
+constexpr int kMaxT = kMaxK;  // monomial columns that fit next to 3r trig columns
+constexpr int kMaxPairs = kMaxR * (kMaxR + 1) / 2;
+// per-CTA scalar partials (double): [0] sum r^2, [1 .. 1+r*r) Phi^T Phi, [1+r*r .. +3r) d omega
+constexpr int kScal = 1 + kMaxR * kMaxR + 3 * kMaxR;
+constexpr int kMaxSlots = 2048;
+
+// Column order of POOL_DATA (CYL:376-434): idx[j][0..deg[j]) are the mode indices multiplied left to right.
+// Passed by value in kernel parameters (constant bank, uniform access).
+struct MonoTable {
+    int8_t idx[kMaxT][kMaxP + 1];
+    int8_t deg[kMaxT];
+};
+
+struct Workspace {  // device-side carve-up of the caller's workspace; computed identically on the host
+    float* Epart;    // [slots_x][Kp][mld]
+    double* Spart;   // [kMaxSlots][kScal]
+    float* Dacc;     // [Kp][ld]   (only when the time axis is chunked)
+    float* l1;       // [1] sum |gates| before the update
+    float* tc;       // tcgen05 path scratch (W hi/lo etc.)
+    size_t bytes;
+};
+
+struct UpdateArgs {
+    const float* red;   // [Kp*mld | loss | gram r*r | domega 3r]
+    const float* dphi;  // [r][ld]  (apply mode: read; grads mode: completed in place with the ortho term)
+    float* dphi_out;
+    const float* P;
+    float* phi; float* phi_m; float* phi_u;
+    float* gates; float* gates_m; float* gates_u;
+    float* rows; float* rows_m; float* rows_u;
+    float* coefs; float* coefs_m; float* coefs_u;
+    float* periods; float* periods_m; float* periods_u;
+    float* omega; float* omega_m; float* omega_u;
+    float* d_gates; float* d_rows; float* d_coefs; float* d_periods; float* d_omega;  // grads mode outputs
+    const float* hyper;
+    const int32_t* step_dev;
+    const float* l1_in;
+    float* losses_out;
+    long long n, ld;
+    double inv_nm;  // 1 / (n_global * m)
+    int m, mld, r, K, Kp, nF;
+    int apply;      // 1 = Adamax in place, 0 = write gradients
+};
+
+struct EvalArgs {
+    const float* P;
+    const float* phi;
+    const float* omega;
+    const float* W;
+    float* out;
+    long long n, ld;
+    int m, mld, r, T, K;
+    MonoTable mt;
+};
+
+// host-side launchers (one per translation unit)
+int build_w(const desmo_shape* s, int K, int Kp, const float* gates, float* rows, const float* coefs, const float* periods,
+            float* W, float* Whi, float* Wlo, int32_t* step_dev, float* l1_out, cudaStream_t st);
+int fused_fp32(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const float* U, const float* P, const float* phi,
+               const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st);
+int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const float* U, const float* P, const float* phi,
+             const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st);
+int fused_tc_supported(const desmo_shape* s, int Kp);
+int launch_update(const UpdateArgs& a, cudaStream_t st);
+int launch_reconstruct(const EvalArgs& a, cudaStream_t st);
+int launch_colnorm2(const EvalArgs& a, cudaStream_t st);
+int pod_gram_fp32(const desmo_shape* s, const float* U, float* C, cudaStream_t st);
+int pod_gram_tc(const desmo_shape* s, const float* U, float* C, void* workspace, cudaStream_t st);
+int pod_eig(int m, int r, const float* C, float* V, float* sigma, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int pod_project(const desmo_shape* s, const float* U, const float* V, const float* sigma, float* P, cudaStream_t st);
+
+struct Dims { int T, K, Kp; MonoTable mt; };
+int validate_shape(const desmo_shape* s, Dims* d);
+int carve_workspace(const desmo_shape* s, const Dims& d, void* base, Workspace* ws);
+bool use_tc_path(const desmo_shape* s, const Dims& d);
+
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+int build_mono_table(int r, int p, MonoTable* mt);  // returns T or <0
+int device_ok();
+
+#define DESMO_CUDA(call)                                   \
+    do {                                                   \
+        int _rc = ::desmo::check_cuda((call), #call);      \
+        if (_rc) return _rc;                               \
+    } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// One library column of G at a point: Phi[] is read through a strided smem column (dynamic mode index).
+__device__ __forceinline__ float monomial(const MonoTable& mt, int j, const float* phi_col, int stride) {
+    const int deg = mt.deg[j];
+    float v = 1.0f;
+    for (int q = 0; q < deg; ++q) {
+        const float f = phi_col[mt.idx[j][q] * stride];
+        v = (q == 0) ? f : v * f;  // left-to-right products, as CYL:390-431
+    }
+    return v;
+}
+
+// Chain rule D (n x K, already scaled by 2/(n_global m)) -> d mse/d Phi_i, d mse/d omega, Phi^T Phi contributions of ONE point.
+// phi_col / d_col / dphi_col are smem columns of this point (element i at [i*stride]).  Returns nothing; writes
+// dphi_col[i] (i<r) and adds this point's d omega terms into dom[3r] (registers of the caller, static indexing
+// avoided by going through smem in the callers).
+__device__ __forceinline__ void chain_rule_point(const MonoTable& mt, int r, int T, const float* __restrict__ omega,
+                                                 const float* phi_col, const float* d_col, float* dphi_col, float* dom_col,
+                                                 int stride) {
+    for (int i = 0; i < r; ++i) dphi_col[i * stride] = 0.0f;
+    for (int j = 1; j < T; ++j) {  // j = 0 is the constant column
+        const int deg = mt.deg[j];
+        const float dj = d_col[j * stride];
+        for (int pos = 0; pos < deg; ++pos) {
+            float rest = 1.0f;
+            for (int q = 0; q < deg; ++q)
+                if (q != pos) rest *= phi_col[mt.idx[j][q] * stride];
+            dphi_col[mt.idx[j][pos] * stride] += dj * rest;
+        }
+    }
+    for (int i = 0; i < r; ++i) {
+        const float ph = phi_col[i * stride];
+        const float ws = omega[3 * i], wc = omega[3 * i + 1], wh = omega[3 * i + 2];
+        const float ds = d_col[(T + i) * stride], dc = d_col[(T + r + i) * stride], dh = d_col[(T + 2 * r + i) * stride];
+        const float cs = cosf(ws * ph);            // d sin(w phi)
+        const float sn = sinf(wc * ph);            // -d cos(w phi)
+        const float th = tanhf(wh * ph);
+        const float sech2 = 1.0f - th * th;
+        dphi_col[i * stride] += ds * ws * cs - dc * wc * sn + dh * wh * sech2;
+        dom_col[(3 * i) * stride] = ds * ph * cs;
+        dom_col[(3 * i + 1) * stride] = -dc * ph * sn;
+        dom_col[(3 * i + 2) * stride] = dh * ph * sech2;
+    }
+}
+
+}  // namespace desmo

@@ -1,0 +1,383 @@
+// Fused residual + gradient pass, FP32 FFMA path (DESMO_PATH_FP32).
+//
+// One pass over U (time-major [m][ld]).  A CTA owns tiles of 256 mesh points (one point per thread) and one time chunk
+// [tc0, tc0+mc); it walks the chunk in slabs of 16 snapshots:
+//   B1  rec[t]   = sum_k g[k] W[k][t]            g = the thread's own library row, kept in registers   (CYL:548,565-572)
+//       r[t]     = rec[t] - U[t][x]               (R is never written to global memory)                 (CYL:722)
+//   B2  d[k]    += r[t] W[k][t]                   d = the thread's row of dG = R W^T, in registers
+//   B3  E[k][t] += sum_x G[x][k] r[x][t]          cross-thread: R slab + G tile staged in smem, E chunk resident in smem
+// After the last slab the chain rule through POOL_DATA / sin / cos / tanh / (phi * POD) is applied in place (single
+// chunk) or d is accumulated to Dacc for the chain-rule kernel (chunked time axis, large K*m).
+#include "common.cuh"
+
+namespace desmo {
+
+constexpr int kTile = 256;  // points per CTA tile == threads
+constexpr int kGS = 260;    // smem row pitch of G_s / R_s (float4-aligned, rows shift by one 16B bank group)
+constexpr int kBT = 16;     // snapshots per slab
+
+struct FusedArgs {
+    const float* U;
+    const float* P;
+    const float* phi;
+    const float* omega;
+    const float* W;
+    float* dphi;
+    float* Epart;
+    double* Spart;
+    float* Dacc;
+    long long n, ld;
+    int m, mld, r, T, K, nchunk, mc;
+    float scale;  // 2 / (n_global * m)
+    MonoTable mt;
+};
+
+template <int KP>
+struct FusedSmem {
+    static constexpr int red_doubles = 8 * kScal;
+    static constexpr int g_off = 0;
+    static constexpr int r_off = g_off + KP * kGS;
+    static constexpr int scr_off = r_off + kBT * kGS;
+    static constexpr int wt_off = scr_off + 8 * kBT * KP;
+    static constexpr int phi_off = wt_off + 2 * kBT * KP;
+    static constexpr int dphi_off = phi_off + kMaxR * kGS;
+    static constexpr int e_off = dphi_off + kMaxR * kGS;
+    // chain-rule scratch dom_s[3r][kGS] aliases R_s..Wt_s, which are dead by then
+    static_assert(3 * kMaxR * kGS <= phi_off - r_off, "dom_s alias does not fit");
+    static size_t bytes(int mc) { return red_doubles * sizeof(double) + (size_t)(e_off + KP * mc) * sizeof(float); }
+};
+
+template <int KP>
+__global__ void __launch_bounds__(kTile, 1) fused_fp32_kernel(const FusedArgs a) {
+    using L = FusedSmem<KP>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* red_s = reinterpret_cast<double*>(smem_raw);
+    float* fs = reinterpret_cast<float*>(smem_raw + L::red_doubles * sizeof(double));
+    float* G_s = fs + L::g_off;      // [KP][kGS]   (re-used as D_s for the chain rule)
+    float* R_s = fs + L::r_off;      // [kBT][kGS]  (R_s+scr re-used as dom_s[3r][kTile] for the chain rule)
+    float* scr = fs + L::scr_off;    // [8][kBT*KP]
+    float* Wt_s = fs + L::wt_off;    // [2][kBT][KP]
+    float* Phi_s = fs + L::phi_off;  // [kMaxR][kGS]
+    float* dPhi_s = fs + L::dphi_off;
+    float* E_s = fs + L::e_off;      // [KP][mc]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = a.r, T = a.T, K = a.K, mc = a.mc;
+    const int tc0 = blockIdx.y * mc;
+    const int tc1 = min(tc0 + mc, a.mld);
+    const bool single = (a.nchunk == 1);
+    const long long ntiles = (a.ld + kTile - 1) / kTile;
+
+    for (int i = tid; i < KP * mc; i += kTile) E_s[i] = 0.0f;
+    for (int i = tid; i < L::red_doubles; i += kTile) red_s[i] = 0.0;
+    double loss_acc = 0.0;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long x = tile * kTile + tid;
+        const bool xin = x < a.n;
+        // ---- library row of this point (CYL:538-548,565-567) ----
+        for (int i = 0; i < r; ++i) {
+            float v = 0.0f;
+            if (x < a.ld) v = a.phi[(long long)i * a.ld + x] * a.P[(long long)i * a.ld + x];
+            Phi_s[i * kGS + tid] = v;
+        }
+        float g[KP], d[KP];
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            float v = 0.0f;
+            if (j < T) {
+                v = monomial(a.mt, j, Phi_s + tid, kGS);
+            } else if (j < K) {
+                const int b = (j - T) / r, i = (j - T) - b * r;
+                const float arg = a.omega[3 * i + b] * Phi_s[i * kGS + tid];
+                v = (b == 0) ? sinf(arg) : (b == 1) ? cosf(arg) : tanhf(arg);
+            }
+            g[j] = v;
+            d[j] = 0.0f;
+            G_s[j * kGS + tid] = v;
+        }
+        // W slab 0 of this chunk
+        for (int i = tid; i < kBT * KP; i += kTile) {
+            const int k = i / kBT, tt = i % kBT;
+            Wt_s[tt * KP + k] = a.W[(long long)k * a.mld + tc0 + tt];
+        }
+        __syncthreads();
+
+        int buf = 0;
+        for (int t0 = tc0; t0 < tc1; t0 += kBT, buf ^= 1) {
+            // prefetch next W slab into the other buffer (visible after this slab's barriers)
+            if (t0 + kBT < tc1) {
+                for (int i = tid; i < kBT * KP; i += kTile) {
+                    const int k = i / kBT, tt = i % kBT;
+                    Wt_s[(buf ^ 1) * kBT * KP + tt * KP + k] = a.W[(long long)k * a.mld + t0 + kBT + tt];
+                }
+            }
+            float u[kBT];
+#pragma unroll
+            for (int tt = 0; tt < kBT; ++tt) {
+                const int t = t0 + tt;
+                u[tt] = (xin && t < a.m) ? __ldg(a.U + (long long)t * a.ld + x) : 0.0f;
+            }
+            const float* Wb = Wt_s + buf * kBT * KP;
+            float lsum = 0.0f;
+#pragma unroll
+            for (int tg = 0; tg < kBT / 4; ++tg) {
+                float rec[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int kc = 0; kc < KP / 4; ++kc) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 w = *reinterpret_cast<const float4*>(Wb + (tg * 4 + j) * KP + kc * 4);
+                        rec[j] = fmaf(g[kc * 4 + 0], w.x, rec[j]);
+                        rec[j] = fmaf(g[kc * 4 + 1], w.y, rec[j]);
+                        rec[j] = fmaf(g[kc * 4 + 2], w.z, rec[j]);
+                        rec[j] = fmaf(g[kc * 4 + 3], w.w, rec[j]);
+                    }
+                }
+                float rr[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int t = t0 + tg * 4 + j;
+                    rr[j] = (xin && t < a.m) ? rec[j] - u[tg * 4 + j] : 0.0f;
+                    lsum = fmaf(rr[j], rr[j], lsum);
+                    R_s[(tg * 4 + j) * kGS + tid] = rr[j];
+                }
+#pragma unroll
+                for (int kc = 0; kc < KP / 4; ++kc) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 w = *reinterpret_cast<const float4*>(Wb + (tg * 4 + j) * KP + kc * 4);
+                        d[kc * 4 + 0] = fmaf(rr[j], w.x, d[kc * 4 + 0]);
+                        d[kc * 4 + 1] = fmaf(rr[j], w.y, d[kc * 4 + 1]);
+                        d[kc * 4 + 2] = fmaf(rr[j], w.z, d[kc * 4 + 2]);
+                        d[kc * 4 + 3] = fmaf(rr[j], w.w, d[kc * 4 + 3]);
+                    }
+                }
+            }
+            loss_acc += (double)lsum;
+            __syncthreads();  // R_s complete
+
+            // ---- B3: E slab partial over this warp's 32-point segment ----
+            {
+                const int kg = lane >> 2, tl = lane & 3, p0 = warp * 32;
+                float acc[KP / 8][4];
+#pragma unroll
+                for (int i = 0; i < KP / 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+#pragma unroll 2
+                for (int pc = 0; pc < 8; ++pc) {
+                    float4 rv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        rv[j] = *reinterpret_cast<const float4*>(R_s + (tl + 4 * j) * kGS + p0 + pc * 4);
+#pragma unroll
+                    for (int i = 0; i < KP / 8; ++i) {
+                        const float4 gv = *reinterpret_cast<const float4*>(G_s + (kg + 8 * i) * kGS + p0 + pc * 4);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            acc[i][j] = fmaf(gv.x, rv[j].x, acc[i][j]);
+                            acc[i][j] = fmaf(gv.y, rv[j].y, acc[i][j]);
+                            acc[i][j] = fmaf(gv.z, rv[j].z, acc[i][j]);
+                            acc[i][j] = fmaf(gv.w, rv[j].w, acc[i][j]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < KP / 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) scr[warp * kBT * KP + (kg + 8 * i) * kBT + tl + 4 * j] = acc[i][j];
+            }
+            __syncthreads();  // scr complete, R_s free
+            for (int o = tid; o < KP * kBT; o += kTile) {
+                float s = 0.0f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) s += scr[w * kBT * KP + o];
+                const int k = o / kBT, tt = o % kBT;
+                E_s[k * mc + (t0 - tc0) + tt] += s;
+            }
+            // next slab's first barrier orders these scr reads before scr is rewritten
+        }
+        __syncthreads();  // all B3 reads of G_s done
+
+        if (single) {
+            float* D_s = G_s;
+            float* dom_s = R_s;
+#pragma unroll
+            for (int j = 0; j < KP; ++j) D_s[j * kGS + tid] = d[j] * a.scale;
+            chain_rule_point(a.mt, r, T, a.omega, Phi_s + tid, D_s + tid, dPhi_s + tid, dom_s + tid, kGS);
+            for (int i = 0; i < r; ++i)
+                if (x < a.ld) a.dphi[(long long)i * a.ld + x] = dPhi_s[i * kGS + tid] * a.P[(long long)i * a.ld + x];
+            for (int i = 0; i < 3 * r; ++i) {
+                const float v = warp_sum(xin ? dom_s[i * kGS + tid] : 0.0f);
+                if (lane == 0) red_s[warp * kScal + 1 + kMaxR * kMaxR + i] += (double)v;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < KP; ++j)
+                if (j < K && xin) atomicAdd(a.Dacc + (long long)j * a.ld + x, d[j]);
+        }
+        if (single) {
+            for (int i = 0; i < r; ++i)
+                for (int j = i; j < r; ++j) {
+                    const float v = warp_sum(Phi_s[i * kGS + tid] * Phi_s[j * kGS + tid]);
+                    if (lane == 0) red_s[warp * kScal + 1 + i * kMaxR + j] += (double)v;
+                }
+        }
+        __syncthreads();  // before the next tile overwrites Phi_s / G_s
+    }
+
+    // ---- flush ----
+    loss_acc = warp_sum(loss_acc);
+    if (lane == 0) red_s[warp * kScal + 0] = loss_acc;
+    __syncthreads();
+    const int slot = blockIdx.y * gridDim.x + blockIdx.x;
+    for (int i = tid; i < kScal; i += kTile) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += red_s[w * kScal + i];
+        a.Spart[(long long)slot * kScal + i] = s;
+    }
+    float* Eo = a.Epart + (long long)blockIdx.x * KP * a.mld;
+    const int width = tc1 - tc0;
+    for (int i = tid; i < KP * width; i += kTile) {
+        const int k = i / width, tt = i % width;
+        Eo[(long long)k * a.mld + tc0 + tt] = E_s[k * mc + tt];
+    }
+}
+
+// Chain rule for the chunked path: Dacc [Kp][ld] (unscaled) -> dphi, d omega, Phi^T Phi partials.
+__global__ void __launch_bounds__(kTile) chain_rule_kernel(const FusedArgs a, int slot_base) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* red_s = reinterpret_cast<double*>(smem_raw);
+    float* fs = reinterpret_cast<float*>(smem_raw + 8 * kScal * sizeof(double));
+    float* Phi_s = fs;                         // [kMaxR][kTile]
+    float* dPhi_s = Phi_s + kMaxR * kTile;     // [kMaxR][kTile]
+    float* dom_s = dPhi_s + kMaxR * kTile;     // [3*kMaxR][kTile]
+    float* D_s = dom_s + 3 * kMaxR * kTile;    // [K][kTile]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = a.r, T = a.T, K = a.K;
+    for (int i = tid; i < 8 * kScal; i += kTile) red_s[i] = 0.0;
+    __syncthreads();
+    const long long ntiles = (a.ld + kTile - 1) / kTile;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long x = tile * kTile + tid;
+        const bool xin = x < a.n;
+        for (int i = 0; i < r; ++i)
+            Phi_s[i * kTile + tid] = (x < a.ld) ? a.phi[(long long)i * a.ld + x] * a.P[(long long)i * a.ld + x] : 0.0f;
+        for (int j = 0; j < K; ++j) D_s[j * kTile + tid] = xin ? a.Dacc[(long long)j * a.ld + x] * a.scale : 0.0f;
+        chain_rule_point(a.mt, r, T, a.omega, Phi_s + tid, D_s + tid, dPhi_s + tid, dom_s + tid, kTile);
+        for (int i = 0; i < r; ++i)
+            if (x < a.ld) a.dphi[(long long)i * a.ld + x] = dPhi_s[i * kTile + tid] * a.P[(long long)i * a.ld + x];
+        for (int i = 0; i < 3 * r; ++i) {
+            const float v = warp_sum(xin ? dom_s[i * kTile + tid] : 0.0f);
+            if (lane == 0) red_s[warp * kScal + 1 + kMaxR * kMaxR + i] += (double)v;
+        }
+        for (int i = 0; i < r; ++i)
+            for (int j = i; j < r; ++j) {
+                const float v = warp_sum(Phi_s[i * kTile + tid] * Phi_s[j * kTile + tid]);
+                if (lane == 0) red_s[warp * kScal + 1 + i * kMaxR + j] += (double)v;
+            }
+    }
+    __syncthreads();
+    for (int i = tid; i < kScal; i += kTile) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += red_s[w * kScal + i];
+        a.Spart[(long long)(slot_base + blockIdx.x) * kScal + i] = s;
+    }
+}
+
+// Deterministic second stage: sum the per-CTA partials in a fixed order into `red`.
+__global__ void reduce_partials_kernel(const float* __restrict__ Epart, int nx, long long ecount,
+                                       const double* __restrict__ Spart, int nslots, int r, float* __restrict__ red) {
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o < ecount) {
+        float s = 0.0f;
+        for (int b = 0; b < nx; ++b) s += Epart[(long long)b * ecount + o];
+        red[o] = s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < kScal) {
+        const int i = threadIdx.x;
+        double s = 0.0;
+        for (int b = 0; b < nslots; ++b) s += Spart[(long long)b * kScal + i];
+        // compact layout: [loss | gram r*r | domega 3r]
+        if (i == 0) {
+            red[ecount] = (float)s;
+        } else if (i < 1 + kMaxR * kMaxR) {
+            const int gi = (i - 1) / kMaxR, gj = (i - 1) % kMaxR;
+            if (gi < r && gj < r && gi <= gj) {
+                red[ecount + 1 + gi * r + gj] = (float)s;
+                red[ecount + 1 + gj * r + gi] = (float)s;
+            }
+        } else {
+            const int w = i - 1 - kMaxR * kMaxR;
+            if (w < 3 * r) red[ecount + 1 + r * r + w] = (float)s;
+        }
+    }
+}
+
+template <int KP>
+static int launch_fused(const FusedArgs& a, int sms, size_t smem_cap, cudaStream_t st, int* gx_out, int* nslots_out) {
+    using L = FusedSmem<KP>;
+    // smallest number of time chunks whose E chunk fits next to the staging buffers
+    int nchunk = 1, mc = a.mld;
+    while (L::bytes(mc) > smem_cap) {
+        ++nchunk;
+        mc = (((a.mld + nchunk - 1) / nchunk) + kBT - 1) / kBT * kBT;
+        if (mc <= kBT) {
+            set_error("fused_fp32: shape does not fit shared memory");
+            return DESMO_ERR_UNSUPPORTED;
+        }
+    }
+    nchunk = (a.mld + mc - 1) / mc;
+    FusedArgs b = a;
+    b.nchunk = nchunk;
+    b.mc = mc;
+    const long long ntiles = (a.ld + kTile - 1) / kTile;
+    const int per_chunk = sms / nchunk > 0 ? sms / nchunk : 1;
+    const int gx = (int)(ntiles < per_chunk ? ntiles : per_chunk);
+    DESMO_CUDA(cudaFuncSetAttribute(fused_fp32_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes(mc)));
+    if (nchunk > 1) DESMO_CUDA(cudaMemsetAsync(b.Dacc, 0, sizeof(float) * (size_t)KP * a.ld, st));
+    fused_fp32_kernel<KP><<<dim3(gx, nchunk), kTile, L::bytes(mc), st>>>(b);
+    DESMO_CUDA(cudaGetLastError());
+    int nslots = gx * nchunk;
+    if (nchunk > 1) {
+        const int gc = (int)(ntiles < 256 ? ntiles : 256);
+        const size_t sm = 8 * kScal * sizeof(double) + (size_t)(5 * kMaxR + a.K) * kTile * sizeof(float);
+        DESMO_CUDA(cudaFuncSetAttribute(chain_rule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        chain_rule_kernel<<<gc, kTile, sm, st>>>(b, nslots);
+        DESMO_CUDA(cudaGetLastError());
+        nslots += gc;
+    }
+    *gx_out = gx;
+    *nslots_out = nslots;
+    return DESMO_OK;
+}
+
+int fused_fp32(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const float* U, const float* P, const float* phi,
+               const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st) {
+    int dev = 0, sms = 0, smem_cap = 0;
+    DESMO_CUDA(cudaGetDevice(&dev));
+    DESMO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DESMO_CUDA(cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    FusedArgs a{};
+    a.U = U; a.P = P; a.phi = phi; a.omega = omega; a.W = W; a.dphi = dphi;
+    a.Epart = ws.Epart; a.Spart = ws.Spart; a.Dacc = ws.Dacc;
+    a.n = s->n; a.ld = s->ld; a.m = s->m; a.mld = s->mld; a.r = s->r; a.T = T; a.K = T + 3 * s->r;
+    a.scale = (float)(2.0 / ((double)s->n_global * (double)s->m));
+    a.mt = mt;
+    int gx = 0, nslots = 0, rc = 0;
+    switch (Kp) {
+        case 16: rc = launch_fused<16>(a, sms, smem_cap, st, &gx, &nslots); break;
+        case 32: rc = launch_fused<32>(a, sms, smem_cap, st, &gx, &nslots); break;
+        case 48: rc = launch_fused<48>(a, sms, smem_cap, st, &gx, &nslots); break;
+        case 64: rc = launch_fused<64>(a, sms, smem_cap, st, &gx, &nslots); break;
+        default: set_error("fused_fp32: padded K=%d not instantiated", Kp); return DESMO_ERR_UNSUPPORTED;
+    }
+    if (rc) return rc;
+    const long long ecount = (long long)Kp * s->mld;
+    reduce_partials_kernel<<<(unsigned)((ecount + 255) / 256), 256, 0, st>>>(ws.Epart, gx, ecount, ws.Spart, nslots, s->r, red);
+    DESMO_CUDA(cudaGetLastError());
+    return DESMO_OK;
+}
+
+}  // namespace desmo

@@ -1,0 +1,178 @@
+// Loss assembly, regulariser sub-gradients and the Adamax update for every parameter, one launch.
+//   gates/rows/omega(/coefs/periods) are replicated on every rank and updated identically from the all-reduced `red`;
+//   phi is the rank's own slab.  Reference: CYL:714-733 (losses), CYL:766 (autograd of the regularisers),
+//   torch.optim.Adamax (_single_tensor_adamax): m += (1-b1)(g-m); u = max(b2*u, |g|+eps); p -= lr/(1-b1^t) * m/u.
+#include "common.cuh"
+
+namespace desmo {
+
+__device__ __forceinline__ float sgn(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
+
+__device__ __forceinline__ void adamax(float* p, float* m, float* u, float g, float clr) {
+    float mm = *m, uu = *u;
+    mm = mm + 0.1f * (g - mm);                        // exp_avg.lerp_(grad, 1 - beta1)
+    uu = fmaxf(uu * 0.999f, fabsf(g) + 1e-8f);        // max(beta2 * exp_inf, |grad| + eps)
+    *m = mm;
+    *u = uu;
+    *p = *p - clr * mm / uu;                          // addcdiv_(exp_avg, exp_inf, value=-clr)
+}
+
+__device__ __forceinline__ float clr_of(float lr, int step) {
+    const double bc = 1.0 - pow(0.9, (double)step);
+    return (float)((double)lr / bc);
+}
+
+__device__ float block_sum(float v, float* sh) {  // blockDim.x == 256
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sh[w];
+    return s;
+}
+
+__device__ __forceinline__ float t_point_u(int t, int m) {
+    const float step = __fdiv_rn((float)m, (float)(m - 1));
+    return (t < m / 2) ? __fmul_rn(step, (float)t) : __fsub_rn((float)m, __fmul_rn(step, (float)(m - 1 - t)));
+}
+
+__global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
+    __shared__ float sh[8];
+    __shared__ float gsign[kMaxR * kMaxR];
+    __shared__ float cgrad[2 * 64 + 2];
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x;
+    const int step = a.apply ? *a.step_dev : 1;
+    const float scale = (float)(2.0 * a.inv_nm);
+    const float lam = a.hyper[DESMO_HYP_L1_LAMBDA];
+    const long long eoff = (long long)a.Kp * a.mld;
+
+    if (b < a.K) {
+        // ---------------- one library term: temporal row + its gate ----------------
+        const int k = b;
+        const float gate = a.gates[k];
+        const float* E = a.red + (long long)k * a.mld;
+        float* row = a.rows + (long long)k * a.mld;
+        float acc = 0.0f;
+        if (a.nF == 0) {
+            const float clr = clr_of(a.hyper[DESMO_HYP_LR_Z], step);
+            for (int t = tid; t < a.m; t += 256) {
+                const float e = scale * E[t];
+                acc = fmaf(row[t], e, acc);
+                const float g = gate * e;
+                if (a.apply) adamax(row + t, a.rows_m + (long long)k * a.mld + t, a.rows_u + (long long)k * a.mld + t, g, clr);
+                else a.d_rows[(long long)k * a.mld + t] = g;
+            }
+        } else {
+            const int nF = a.nF, width = 2 * nF + 1;
+            const float period = a.periods[k];
+            const float* c = a.coefs + (long long)k * width;
+            float a0 = 0.0f, dper = 0.0f;
+            for (int t = tid; t < a.m; t += 256) {
+                const float e = scale * E[t];
+                acc = fmaf(row[t], e, acc);
+                a0 += gate * e;
+            }
+            a0 = block_sum(a0, sh);
+            if (tid == 0) cgrad[0] = a0;
+            for (int h = 1; h <= nF; ++h) {
+                float ca = 0.0f, sa = 0.0f;
+                const float two_pi_h = (float)(6.283185307179586 * (double)h);
+                const float ah = c[2 * h - 1], bh = c[2 * h];
+                for (int t = tid; t < a.m; t += 256) {
+                    const float dz = gate * (scale * E[t]);
+                    const float th = __fdiv_rn(__fmul_rn(two_pi_h, t_point_u(t, a.m)), period);
+                    const float cs = cosf(th), sn = sinf(th);
+                    ca = fmaf(dz, cs, ca);
+                    sa = fmaf(dz, sn, sa);
+                    dper = fmaf(dz * (th / period), ah * sn - bh * cs, dper);  // d theta / d period = -theta / period
+                }
+                ca = block_sum(ca, sh);
+                sa = block_sum(sa, sh);
+                if (tid == 0) { cgrad[2 * h - 1] = ca; cgrad[2 * h] = sa; }
+            }
+            dper = block_sum(dper, sh);
+            __syncthreads();
+            if (tid < width) {
+                if (a.apply) adamax(a.coefs + (long long)k * width + tid, a.coefs_m + (long long)k * width + tid,
+                                    a.coefs_u + (long long)k * width + tid, cgrad[tid], clr_of(a.hyper[DESMO_HYP_LR_Z], step));
+                else a.d_coefs[(long long)k * width + tid] = cgrad[tid];
+            }
+            if (tid == 0) {
+                if (a.apply) adamax(a.periods + k, a.periods_m + k, a.periods_u + k, dper, clr_of(a.hyper[DESMO_HYP_LR_PERIOD], step));
+                else a.d_periods[k] = dper;
+            }
+        }
+        acc = block_sum(acc, sh);
+        if (tid == 0) {
+            const float g = acc + lam * sgn(gate);  // d/dgate [mse + l1_lambda * |gate|]
+            if (a.apply) adamax(a.gates + k, a.gates_m + k, a.gates_u + k, g, clr_of(a.hyper[DESMO_HYP_LR_GATES], step));
+            else a.d_gates[k] = g;
+        }
+    } else if (b == a.K) {
+        // ---------------- omega + the three printed losses ----------------
+        const int r = a.r;
+        if (tid < 3 * r) {
+            const float g = a.red[eoff + 1 + r * r + tid];
+            if (a.apply) adamax(a.omega + tid, a.omega_m + tid, a.omega_u + tid, g, clr_of(a.hyper[DESMO_HYP_LR_OMEGA], step));
+            else a.d_omega[tid] = g;
+        }
+        if (tid == 0 && a.losses_out) {
+            const float mse = (float)((double)a.red[eoff] * a.inv_nm);
+            float ortho = 0.0f;
+            for (int i = 0; i < r; ++i)
+                for (int j = i + 1; j < r; ++j) ortho += fabsf(a.red[eoff + 1 + i * r + j]);
+            const float l1 = *a.l1_in;
+            a.losses_out[0] = mse;
+            a.losses_out[1] = ortho;
+            a.losses_out[2] = l1;
+            a.losses_out[3] = mse + a.hyper[DESMO_HYP_BETA] * ortho + lam * l1;
+        }
+    } else {
+        // ---------------- phi slab: ortho sub-gradient + update ----------------
+        const int r = a.r;
+        if (tid < r * r) {
+            const int i = tid / r, j = tid % r;
+            gsign[tid] = (i == j) ? 0.0f : sgn(a.red[eoff + 1 + tid]);  // d|Phi_i.Phi_j| = sign(dot)
+        }
+        __syncthreads();
+        const float beta = a.hyper[DESMO_HYP_BETA];
+        const float clr = clr_of(a.hyper[DESMO_HYP_LR_PHI], step);
+        const long long nb = gridDim.x - a.K - 1;
+        for (long long x = (long long)(b - a.K - 1) * 256 + tid; x < a.n; x += nb * 256) {
+            float lat[kMaxR], pod[kMaxR];
+#pragma unroll
+            for (int i = 0; i < kMaxR; ++i) {
+                pod[i] = (i < r) ? a.P[(long long)i * a.ld + x] : 0.0f;
+                lat[i] = (i < r) ? a.phi[(long long)i * a.ld + x] * pod[i] : 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < kMaxR; ++i) {
+                if (i < r) {
+                    float o = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < kMaxR; ++j)
+                        if (j < r) o = fmaf(gsign[i * r + j], lat[j], o);
+                    const float g = a.dphi[(long long)i * a.ld + x] + beta * o * pod[i];
+                    if (a.apply) adamax(a.phi + (long long)i * a.ld + x, a.phi_m + (long long)i * a.ld + x,
+                                        a.phi_u + (long long)i * a.ld + x, g, clr);
+                    else a.dphi_out[(long long)i * a.ld + x] = g;
+                }
+            }
+        }
+    }
+}
+
+int launch_update(const UpdateArgs& a, cudaStream_t st) {
+    long long nb = (a.n + 255) / 256;
+    if (nb > 148 * 8) nb = 148 * 8;
+    if (nb < 1) nb = 1;
+    if (a.nF > 64) { set_error("update: nF > 64 not supported"); return DESMO_ERR_UNSUPPORTED; }
+    update_kernel<<<(unsigned)(a.K + 1 + nb), 256, 0, st>>>(a);
+    DESMO_CUDA(cudaGetLastError());
+    return DESMO_OK;
+}
+
+}  // namespace desmo

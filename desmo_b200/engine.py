@@ -1,0 +1,214 @@
+"""Device-resident packed state of one DESMO model shard and the per-step launch sequence.
+
+PyTorch is used for memory, streams, CUDA graphs and torch.distributed only; all arithmetic is in libdesmo_b200.so.
+Layout: see include/desmo_b200.h.  One step = build_w -> fused_residual_grad -> [all_reduce(red)] -> adamax_update,
+i.e. the body of the reference loop CYL:711-768 for one full batch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, make_shape, round_up
+
+REFERENCE_LRS = (1e-2, 1e-3, 1e-2, 1e3, 1e-2)  # gates, phi, z, omega, periods  (CYL:592-612, FCYL:628-631)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class DesmoEngine:
+    def __init__(self, n: int, m: int, polyorder: int, r: int, omega_init: float = 10000.0, nF: Optional[int] = None,
+                 period_init: float = 60.0, device: Optional[torch.device] = None, n_global: Optional[int] = None,
+                 path: int = _lib.PATH_AUTO, process_group=None):
+        self.lib = _lib.load()
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+        if device is None or torch.device(device).type != "cuda":
+            raise _lib.DesmoError("desmo_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.device = torch.device(device)
+        self.n, self.m, self.r, self.polyorder = int(n), int(m), int(r), int(polyorder)
+        self.nF = int(nF) if nF else 0
+        self.T = self.lib.desmo_num_terms(self.r, self.polyorder)
+        if self.T < 0:
+            raise _lib.DesmoError(f"unsupported library r={r} polyorder={polyorder} (K must be <= {_lib.MAX_K})")
+        self.K = self.T + 3 * self.r
+        self.Kp = self.lib.desmo_padded_k(self.r, self.polyorder)
+        self.pg = process_group
+        self.n_global = int(n_global) if n_global else self.n
+        self.shape = make_shape(self.n, self.m, self.r, self.polyorder, self.nF, self.n_global, path)
+        self.ld, self.mld = self.shape.ld, self.shape.mld
+        f32 = dict(dtype=torch.float32, device=self.device)
+        z = lambda *s: torch.zeros(*s, **f32)  # noqa: E731
+        self.U: Optional[torch.Tensor] = None
+        self.P = z(self.r, self.ld)
+        self.phi, self.phi_m, self.phi_u, self.dphi = z(self.r, self.ld), z(self.r, self.ld), z(self.r, self.ld), z(self.r, self.ld)
+        self.phi[:, :self.n] = 1.0
+        self.gates, self.gates_m, self.gates_u = torch.ones(self.K, **f32), z(self.K), z(self.K)
+        self.rows, self.rows_m, self.rows_u = z(self.K, self.mld), z(self.K, self.mld), z(self.K, self.mld)
+        self.coefs = self.coefs_m = self.coefs_u = self.periods = self.periods_m = self.periods_u = None
+        if self.nF:
+            w = 2 * self.nF + 1
+            self.coefs, self.coefs_m, self.coefs_u = torch.ones(self.K, w, **f32), z(self.K, w), z(self.K, w)
+            self.periods, self.periods_m, self.periods_u = torch.full((self.K,), float(period_init), **f32), z(self.K), z(self.K)
+        else:
+            self.rows[:, :self.m] = 1.0
+        self.omega, self.omega_m, self.omega_u = torch.full((3 * self.r,), float(omega_init), **f32), z(3 * self.r), z(3 * self.r)
+        self.W = z(self.Kp, self.mld)
+        self.red = z(int(self.lib.desmo_red_count(C.byref(self.shape))))
+        self.hyper = z(_lib.HYP_COUNT)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.losses = z(4)
+        nbytes = C.c_size_t(0)
+        with torch.cuda.device(self.device):
+            check(self.lib.desmo_workspace_bytes(C.byref(self.shape), C.byref(nbytes)), "desmo_workspace_bytes")
+        self.workspace = torch.zeros(nbytes.value, dtype=torch.uint8, device=self.device)
+        self.launches_per_step = 0
+        self.set_hyper(REFERENCE_LRS, 1e-3, 1e-4)
+
+    # ------------------------------------------------------------------ inputs
+    def set_pod_modes(self, pod_modes) -> None:
+        """POD_modes[:, :r] (n x >=r, numpy fp64 or tensor) -> fp32 mode-major, as CYL:538-541 casts them per forward."""
+        pm = torch.as_tensor(np.asarray(pod_modes)[:, :self.r] if not torch.is_tensor(pod_modes) else pod_modes[:, :self.r])
+        if pm.shape != (self.n, self.r):
+            raise ValueError(f"POD modes must be ({self.n}, >={self.r}), got {tuple(pm.shape)}")
+        self.P.zero_()
+        self.P[:, :self.n] = pm.to(torch.float32).t().to(self.device)
+
+    def set_snapshot(self, snapshot: torch.Tensor, non_blocking: bool = True) -> None:
+        """The reference's (m, n) batch (CYL:708).  Host tensors are uploaded; any float dtype is cast to fp32."""
+        if tuple(snapshot.shape) != (self.m, self.n):
+            raise ValueError(f"snapshot must be ({self.m}, {self.n}) like the reference batch, got {tuple(snapshot.shape)}")
+        if self.U is None:
+            self.U = torch.zeros(self.m, self.ld, dtype=torch.float32, device=self.device)
+        self.U[:, :self.n].copy_(snapshot, non_blocking=non_blocking)
+
+    def set_hyper(self, lrs: Sequence[float], beta: float, l1_lambda: float) -> None:
+        vals = list(lrs) + [REFERENCE_LRS[4]] * (5 - len(lrs)) + [beta, l1_lambda]
+        self.hyper_host = [float(v) for v in vals]
+        self.hyper.copy_(torch.tensor(self.hyper_host, dtype=torch.float32), non_blocking=False)
+
+    def reset_optimizer(self) -> None:
+        for t in (self.phi_m, self.phi_u, self.gates_m, self.gates_u, self.rows_m, self.rows_u, self.omega_m, self.omega_u,
+                  self.coefs_m, self.coefs_u, self.periods_m, self.periods_u):
+            if t is not None:
+                t.zero_()
+        self.step_dev.zero_()
+
+    # ------------------------------------------------------------------ launches
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def build_w(self, advance_step: bool = True) -> None:
+        check(self.lib.desmo_build_w(C.byref(self.shape), _ptr(self.gates), _ptr(self.rows), _ptr(self.coefs), _ptr(self.periods),
+                                     _ptr(self.W), _ptr(self.step_dev) if advance_step else None, _ptr(self.workspace),
+                                     self._stream()), "desmo_build_w")
+
+    def fused_residual_grad(self) -> None:
+        if self.U is None:
+            raise _lib.DesmoError("no snapshot matrix set (call set_snapshot)")
+        check(self.lib.desmo_fused_residual_grad(C.byref(self.shape), _ptr(self.U), _ptr(self.P), _ptr(self.phi), _ptr(self.omega),
+                                                 _ptr(self.W), _ptr(self.dphi), _ptr(self.red), _ptr(self.workspace), self._stream()),
+              "desmo_fused_residual_grad")
+
+    def all_reduce(self) -> None:
+        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                   and self.n_global != self.n):
+            torch.distributed.all_reduce(self.red, group=self.pg)
+
+    def adamax_update(self) -> None:
+        check(self.lib.desmo_adamax_update(
+            C.byref(self.shape), _ptr(self.red), _ptr(self.dphi), _ptr(self.P), _ptr(self.phi), _ptr(self.phi_m), _ptr(self.phi_u),
+            _ptr(self.gates), _ptr(self.gates_m), _ptr(self.gates_u), _ptr(self.rows), _ptr(self.rows_m), _ptr(self.rows_u),
+            _ptr(self.coefs), _ptr(self.coefs_m), _ptr(self.coefs_u), _ptr(self.periods), _ptr(self.periods_m), _ptr(self.periods_u),
+            _ptr(self.omega), _ptr(self.omega_m), _ptr(self.omega_u), _ptr(self.hyper), _ptr(self.step_dev), _ptr(self.losses),
+            _ptr(self.workspace), self._stream()), "desmo_adamax_update")
+
+    def train_step(self) -> None:
+        """forward + losses + backward + optimizer.step of CYL:711-768; losses land in self.losses (device)."""
+        with torch.cuda.device(self.device):
+            self.build_w(True)
+            self.fused_residual_grad()
+            self.all_reduce()
+            self.adamax_update()
+
+    def gradients(self, beta: Optional[float] = None, l1_lambda: Optional[float] = None) -> dict:
+        """d total_loss / d every packed parameter (what total_loss.backward() leaves in .grad, CYL:766)."""
+        saved = list(self.hyper_host)
+        if beta is not None or l1_lambda is not None:
+            self.set_hyper(saved[:5], saved[5] if beta is None else beta, saved[6] if l1_lambda is None else l1_lambda)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        g = {"gates": torch.zeros(self.K, **f32), "omega": torch.zeros(3 * self.r, **f32), "phi": torch.zeros(self.r, self.ld, **f32)}
+        if self.nF:
+            g["coefs"], g["periods"] = torch.zeros_like(self.coefs), torch.zeros_like(self.periods)
+        else:
+            g["rows"] = torch.zeros(self.K, self.mld, **f32)
+        with torch.cuda.device(self.device):
+            self.build_w(False)
+            self.fused_residual_grad()
+            self.all_reduce()
+            g["phi"].copy_(self.dphi)
+            check(self.lib.desmo_assemble_grads(
+                C.byref(self.shape), _ptr(self.red), _ptr(g["phi"]), _ptr(self.P), _ptr(self.phi), _ptr(self.gates), _ptr(self.rows),
+                _ptr(self.coefs), _ptr(self.periods), _ptr(self.hyper), _ptr(g["gates"]), _ptr(g.get("rows")), _ptr(g.get("coefs")),
+                _ptr(g.get("periods")), _ptr(g["omega"]), _ptr(self.losses), _ptr(self.workspace), self._stream()),
+                "desmo_assemble_grads")
+        if beta is not None or l1_lambda is not None:
+            self.set_hyper(saved[:5], saved[5], saved[6])
+        g["phi"] = g["phi"][:, :self.n]
+        if "rows" in g:
+            g["rows"] = g["rows"][:, :self.m]
+        return g
+
+    def reconstruct(self) -> torch.Tensor:
+        """recon (m, n) -- first element of forward()'s tuple (CYL:576)."""
+        out = torch.empty(self.m, self.ld, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.build_w(False)
+            check(self.lib.desmo_reconstruct(C.byref(self.shape), _ptr(self.P), _ptr(self.phi), _ptr(self.omega), _ptr(self.W),
+                                             _ptr(out), self._stream()), "desmo_reconstruct")
+        return out[:, :self.n]
+
+    def term_norms(self) -> torch.Tensor:
+        """||gate_j G_j z_j^T||_F = |gate_j| ||G_j|| ||z_j|| for every term (poly_norm / nonlinear_norm, CYL:624-692), K order."""
+        g2 = torch.zeros(self.K, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.build_w(False)  # refreshes rows for the Fourier variant
+            check(self.lib.desmo_library_colnorm2(C.byref(self.shape), _ptr(self.P), _ptr(self.phi), _ptr(self.omega), _ptr(g2),
+                                                  self._stream()), "desmo_library_colnorm2")
+        if self.n_global != self.n and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(g2, group=self.pg)
+        zn = torch.linalg.vector_norm(self.rows[:, :self.m].double(), dim=1)
+        return self.gates.abs().double() * g2.double().sqrt() * zn
+
+    def residual_norm2(self) -> float:
+        """||G W - U||_F^2 over all ranks with the current gates (evaluation pass, no update)."""
+        with torch.cuda.device(self.device):
+            self.build_w(False)
+            self.fused_residual_grad()
+            self.all_reduce()
+        return float(self.red[self.Kp * self.mld].item())
+
+    # ------------------------------------------------------------------ POD (method of snapshots)
+    def pod_from_snapshot(self) -> torch.Tensor:
+        """Replaces POD_analysis (CYL:197-205) for the resident snapshot matrix: returns singular values (r,), fills self.P."""
+        if self.U is None:
+            raise _lib.DesmoError("no snapshot matrix set")
+        f32 = dict(dtype=torch.float32, device=self.device)
+        Cm = torch.zeros(self.m, self.m, **f32)
+        V, sigma = torch.zeros(self.r, self.m, **f32), torch.zeros(self.r, **f32)
+        ws = torch.zeros(2 * 8 * 16 * self.m + 1024, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.desmo_pod_gram(C.byref(self.shape), _ptr(self.U), _ptr(Cm), _ptr(self.workspace), self._stream()), "desmo_pod_gram")
+            if self.n_global != self.n and torch.distributed.is_initialized():
+                torch.distributed.all_reduce(Cm, group=self.pg)
+            check(self.lib.desmo_pod_eig(self.m, self.r, _ptr(Cm), _ptr(V), _ptr(sigma), _ptr(ws), ws.numel(), self._stream()), "desmo_pod_eig")
+            check(self.lib.desmo_pod_project(C.byref(self.shape), _ptr(self.U), _ptr(V), _ptr(sigma), _ptr(self.P), self._stream()),
+                  "desmo_pod_project")
+        self.pod_V, self.pod_gram = V, Cm
+        return sigma

@@ -1,0 +1,107 @@
+"""Training loop of the reference (CYL:592-618,699-786) around the fused step.
+
+Adamax itself runs on the device (desmo_adamax_update).  ReduceLROnPlateau stays on the host exactly as the reference
+configures it (mode='min', factor=0.1, min_lr=1e-6, threshold=1e-4 rel; stepped every ``sched_every`` epochs on the total
+loss -- 10 for CYL/FCYL (CYL:776-778), 1 for TURB/ANEU/FANEU), but the losses are fetched with ONE small D2H copy only
+on the epochs where the reference prints / steps the scheduler, not with an ``.item()`` sync per step (CYL:769).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+
+from .engine import REFERENCE_LRS, DesmoEngine
+
+
+class PlateauScheduler:
+    """torch.optim.lr_scheduler.ReduceLROnPlateau semantics for the engine's 4-5 learning rates."""
+
+    def __init__(self, lrs: Sequence[float], patience: int, factor: float = 0.1, min_lr: float = 1e-6, threshold: float = 1e-4,
+                 eps: float = 1e-8):
+        self.lrs = [float(v) for v in lrs]
+        self.patience, self.factor, self.min_lr, self.threshold, self.eps = patience, factor, min_lr, threshold, eps
+        self.best, self.num_bad = math.inf, 0
+
+    def step(self, metric: float) -> bool:
+        if metric < self.best * (1.0 - self.threshold):
+            self.best, self.num_bad = metric, 0
+        else:
+            self.num_bad += 1
+        changed = False
+        if self.num_bad > self.patience:
+            for i, old in enumerate(self.lrs):
+                new = max(old * self.factor, self.min_lr)
+                if old - new > self.eps:
+                    self.lrs[i] = new
+                    changed = True
+            self.num_bad = 0
+        return changed
+
+
+class DesmoTrainer:
+    def __init__(self, model, lrs: Sequence[float] = REFERENCE_LRS, beta: float = 1e-3, l1_lambda: float = 1e-4,
+                 patience: int = 1000, sched_every: int = 10, use_cuda_graph: bool = True):
+        self.model = model
+        self.engine: DesmoEngine = model.engine if hasattr(model, "engine") else model
+        n_groups = 5 if self.engine.nF else 4
+        self.beta, self.l1_lambda = float(beta), float(l1_lambda)
+        self.scheduler = PlateauScheduler(list(lrs)[:n_groups], patience)
+        self.sched_every = sched_every
+        self.epoch = 0
+        self.history: List[tuple] = []
+        self.engine.set_hyper(self.scheduler.lrs, self.beta, self.l1_lambda)
+        self.use_cuda_graph = use_cuda_graph
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+
+    def _launch(self) -> None:
+        if not self.use_cuda_graph:
+            self.engine.train_step()
+            return
+        if self._graph is None:
+            # warm up once outside capture (function attributes, NCCL communicators), then capture the step
+            e = self.engine
+            snap = {k: getattr(e, k).clone() for k in ("phi", "phi_m", "phi_u", "gates", "gates_m", "gates_u", "rows", "rows_m",
+                                                      "rows_u", "omega", "omega_m", "omega_u", "step_dev")}
+            if e.nF:
+                snap.update({k: getattr(e, k).clone() for k in ("coefs", "coefs_m", "coefs_u", "periods", "periods_m", "periods_u")})
+            side = torch.cuda.Stream(device=e.device)
+            side.wait_stream(torch.cuda.current_stream(e.device))
+            with torch.cuda.stream(side):
+                e.train_step()
+            torch.cuda.current_stream(e.device).wait_stream(side)
+            torch.cuda.synchronize(e.device)
+            for k, v in snap.items():
+                getattr(e, k).copy_(v)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                e.train_step()
+            self._graph = g
+            for k, v in snap.items():  # capture does not execute, but keep state exact regardless
+                getattr(e, k).copy_(v)
+        self._graph.replay()
+
+    def step(self, snapshot: Optional[torch.Tensor] = None) -> Optional[tuple]:
+        """One epoch (CYL:706-778).  Returns (mse, ortho, l1, total) on scheduler epochs, else None (no host sync)."""
+        if snapshot is not None:
+            self.engine.set_snapshot(snapshot)
+        self._launch()
+        out = None
+        if self.epoch % self.sched_every == 0:
+            vals = tuple(float(v) for v in self.engine.losses.tolist())  # the only D2H sync
+            self.history.append((self.epoch, *vals))
+            if self.scheduler.step(vals[3]):
+                self.engine.set_hyper(self.scheduler.lrs, self.beta, self.l1_lambda)
+            out = vals
+        self.epoch += 1
+        return out
+
+    def fit(self, snapshot: torch.Tensor, epochs: int, log_every: int = 0):
+        self.engine.set_snapshot(snapshot)
+        for _ in range(epochs):
+            vals = self.step()
+            if log_every and vals is not None and (self.epoch - 1) % log_every == 0:
+                print(f"Epoch [{self.epoch}/{epochs}], Rec Loss: {vals[0]:.12f}, Spatial ortho loss: {vals[1]:.8f}, "
+                      f"L1 loss: {vals[2]:.4f} ", flush=True)  # CYL:777
+        return self.history

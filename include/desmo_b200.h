@@ -1,0 +1,159 @@
+/*
+ * desmo_b200 -- C ABI of the B200-native DESMO training hot path (libdesmo_b200.so).
+ *
+ * The reference (amir-cardiolab/DESMO) has no FFI: its boundary is the PyTorch module surface.  Each entry point
+ * below replaces a span of that surface; the cited lines are in /root/reference/DESMO/cylinder_flow/DESMO-Cylinder.py
+ * ("CYL") and /root/reference/DESMO_Fourier/cylinder_flow/DESMO-Cylinder.py ("FCYL").  INTEGRATION.md shows the
+ * reference-side binding (ctypes + torch custom op) a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; device pointers unless the name says "host"; no torch types.
+ *   - every function returns 0 on success, non-zero on error; desmo_last_error() gives the thread-local message.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are stream-ordered and never
+ *     synchronise, except the *_host entry points, which return after their results are in host memory.
+ *   - no CPU fallback: every entry point fails (DESMO_ERR_CUDA) if no sm_100 device is usable.
+ *
+ * Device data layout (all fp32, row pitch in elements)
+ *   U      [m][ld]      snapshot matrix, time-major like the reference's `snapshot` batch (CYL:708); ld >= n, ld % 128 == 0,
+ *                        columns n..ld-1 must be zero.
+ *   P      [r][ld]      POD modes, mode-major (POD_modes[:, i] of CYL:204,538-541), zero in the padding.
+ *   phi    [r][ld]      phi_list[i] (CYL:506); likewise its Adamax state exp_avg / exp_inf.
+ *   gates  [K]          [c_coef (T) | sin_coef (r) | cos_coef (r) | tanh_coef (r)]              (CYL:513,524-526)
+ *   rows   [K][mld]     DESMO: [z_list | zsin | zcos | ztanh] free temporal vectors, mld >= m, mld % 16 == 0 (CYL:516-521)
+ *   coefs  [K][2nF+1]   DESMOFourier: Fourier coefficients of each term, periods [K]             (FCYL:527-534)
+ *   omega  [3r]         reference order: omega[3i+{0,1,2}] = sin/cos/tanh frequency of mode i     (CYL:530,561-563)
+ *   W      [Kp][mld]    gate_k * z_k(t), Kp = K rounded up to 16, rows K..Kp-1 zero.
+ *   K = T + 3r, T = C(r+p, p).  Term order inside K: monomials in combinations_with_replacement order
+ *   (POOL_DATA, CYL:376-434), then sin, cos, tanh blocks.
+ */
+#ifndef DESMO_B200_H
+#define DESMO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DESMO_OK 0
+#define DESMO_ERR_ARG 1       /* bad shape / null pointer / misaligned pitch */
+#define DESMO_ERR_UNSUPPORTED 2 /* (r, p, K, m) outside what the kernels are instantiated for */
+#define DESMO_ERR_CUDA 3      /* CUDA runtime error, no device, or not sm_100 */
+
+#define DESMO_MAX_R 8
+#define DESMO_MAX_P 7
+#define DESMO_MAX_K 64
+
+#define DESMO_PATH_AUTO 0
+#define DESMO_PATH_FP32 1  /* FFMA path */
+#define DESMO_PATH_TC 2    /* tcgen05 3xTF32 path */
+
+typedef struct desmo_shape {
+    int64_t n;        /* mesh points owned by this rank (rows of the reference's X) */
+    int64_t ld;       /* pitch of U / P / phi rows, multiple of 128 */
+    int64_t n_global; /* points over all ranks: the MSE is a mean over n_global*m (CYL:722) */
+    int32_t m;        /* snapshots */
+    int32_t mld;      /* pitch of rows / W, multiple of 16 */
+    int32_t r;        /* r_DESMO (CYL:334) */
+    int32_t polyorder;/* CYL:583 */
+    int32_t nF;       /* 0 = DESMO (free temporal vectors); >0 = DESMOFourier with nF harmonics (FCYL:513) */
+    int32_t path;     /* DESMO_PATH_* */
+} desmo_shape;
+
+/* hyper-parameters that live in device memory so that a captured CUDA graph can be replayed while the host-side
+ * ReduceLROnPlateau (CYL:614,778) changes them.  Layout of the `hyper` device array (fp32): */
+enum { DESMO_HYP_LR_GATES = 0, DESMO_HYP_LR_PHI, DESMO_HYP_LR_Z, DESMO_HYP_LR_OMEGA, DESMO_HYP_LR_PERIOD,
+       DESMO_HYP_BETA, DESMO_HYP_L1_LAMBDA, DESMO_HYP_COUNT };
+
+/* layout of the reduction buffer `red` (fp32), the only thing exchanged between ranks (one NCCL all-reduce):
+ *   red[0 .. Kp*mld)                 E = G^T R, unscaled                     ("dA = R^T Phi" of north_star)
+ *   red[Kp*mld + 0]                  sum of squared residuals
+ *   red[Kp*mld + 1 .. +r*r]          Phi^T Phi (row-major r x r)              (ortho term, CYL:714-720)
+ *   red[Kp*mld + 1 + r*r .. +3r]     d mse / d omega, already scaled by 2/(n_global*m), reference order */
+const char* desmo_last_error(void);
+const char* desmo_version(void);
+
+/* T = calculate_number_of_terms(r, p) (CYL:448-455); K = T + 3r; Kp = padded K.  Returns <0 if unsupported. */
+int32_t desmo_num_terms(int32_t r, int32_t polyorder);
+int32_t desmo_padded_k(int32_t r, int32_t polyorder);
+int64_t desmo_red_count(const desmo_shape* s);            /* number of floats in `red` */
+int desmo_workspace_bytes(const desmo_shape* s, size_t* bytes);
+
+/* Library evaluation, temporal side: W = diag(gates) * rows  (CYL:548 `c_coef *`, CYL:565-567 `*_coef_list[i] *`);
+ * with nF > 0 first evaluates rows[k][t] = fourier_series(t_points, period_k, coefs_k) (FCYL:485-506,563,570-572)
+ * into `rows`.  Also advances the device-side Adamax step counter `step_dev` by one (optimizer.step(), CYL:768). */
+int desmo_build_w(const desmo_shape* s, const float* gates, float* rows, const float* coefs, const float* periods,
+                  float* W, int32_t* step_dev, void* workspace, void* stream);
+
+/* The fused pass: streams U once and produces, without materialising R = G(Phi) W - U,
+ *   red    (see above; overwritten, local-rank partial)
+ *   dphi   [r][ld]  d mse / d phi_list (chain rule through POOL_DATA, sin/cos/tanh and phi*POD; ortho term excluded)
+ * Replaces DESMO.forward + MSELoss + the mse part of total_loss.backward() (CYL:535-576,722,766). */
+int desmo_fused_residual_grad(const desmo_shape* s, const float* U, const float* P, const float* phi, const float* omega,
+                              const float* W, float* dphi, float* red, void* workspace, void* stream);
+
+/* Loss assembly + regulariser sub-gradients + Adamax (CYL:714-733,592-612,765-768) for every parameter.
+ * `red` must hold the all-reduced buffer.  losses_out[4] = {mse, ortho, l1, total} of the step just taken
+ * (computed from the pre-update parameters, as CYL:776-777 prints them). */
+int desmo_adamax_update(const desmo_shape* s, const float* red, const float* dphi, const float* P, float* phi,
+                        float* phi_m, float* phi_u, float* gates, float* gates_m, float* gates_u, float* rows,
+                        float* rows_m, float* rows_u, float* coefs, float* coefs_m, float* coefs_u, float* periods,
+                        float* periods_m, float* periods_u, float* omega, float* omega_m, float* omega_u,
+                        const float* hyper, const int32_t* step_dev, float* losses_out, void* workspace, void* stream);
+
+/* Gradients only (for torch.autograd users who keep their own optimizer): fills d_gates[K], d_rows[K][mld]
+ * (or d_coefs / d_periods when nF > 0), d_omega[3r] and completes d_phi with the ortho term. */
+int desmo_assemble_grads(const desmo_shape* s, const float* red, float* dphi, const float* P, const float* phi,
+                         const float* gates, const float* rows, const float* coefs, const float* periods,
+                         const float* hyper, float* d_gates, float* d_rows, float* d_coefs, float* d_periods,
+                         float* d_omega, float* losses_out, void* workspace, void* stream);
+
+/* Materialise recon (the first element of forward()'s 3-tuple, CYL:576) into out[m][ld] -- evaluation only. */
+int desmo_reconstruct(const desmo_shape* s, const float* P, const float* phi, const float* omega, const float* W,
+                      float* out, void* stream);
+
+/* Post-hoc sparsification inputs: squared column norms of G (K floats, local partial; poly_norm/nonlinear_norm
+ * CYL:624-692 use |gate_j| * ||G_j|| * ||z_j||). */
+int desmo_library_colnorm2(const desmo_shape* s, const float* P, const float* phi, const float* omega, float* out_k,
+                           void* stream);
+
+/* POD by the method of snapshots (replaces np.linalg.svd, CYL:197-205):
+ *   gram    C[m][m] = U U^T  (local partial, TF32x3 tensor-core tiles)      -- all-reduce it across ranks
+ *   eig     top-r eigenpairs of C (replicated, on device): sigma[r] = sqrt(lambda), V[r][m]
+ *   project P[i][x] = sum_t U[t][x] V[i][t] / sigma_i, sign-normalised so that the largest-|.| entry of V_i is positive */
+int desmo_pod_gram(const desmo_shape* s, const float* U, float* C, void* workspace, void* stream);
+int desmo_pod_eig(int32_t m, int32_t r, const float* C, float* V, float* sigma, void* workspace, size_t workspace_bytes,
+                  void* stream);
+int desmo_pod_project(const desmo_shape* s, const float* U, const float* V, const float* sigma, float* P, void* stream);
+
+/* Device-resident training session fed from HOST memory (one process of the reference's loop, CYL:706-778).
+ * desmo_session_step_host(snapshot_host) = `snapshot = x[0].type(FloatTensor).to(device)` (CYL:708, pass NULL to keep the
+ * resident copy) + forward/loss/backward/optimizer.step (CYL:711-768) + `loss.item()` (CYL:769): losses_host[4] =
+ * {mse, ortho, l1, total}.  Synchronous. */
+typedef struct desmo_session desmo_session;
+int desmo_session_create(int64_t n, int32_t m, int32_t r, int32_t polyorder, int32_t nF, int32_t path, desmo_session** out);
+int desmo_session_destroy(desmo_session* ss);
+int desmo_session_set_pod_host(desmo_session* ss, const double* pod_host /*[n][r] fp64*/);
+int desmo_session_set_params_host(desmo_session* ss, const float* phi /*[r][n]*/, const float* gates /*[K]*/,
+                                  const float* rows_or_coefs /*[K][m] or [K][2nF+1]*/, const float* periods /*[K] or NULL*/,
+                                  const float* omega /*[3r]*/);
+int desmo_session_set_hyper(desmo_session* ss, const float* lrs /*[5]*/, float beta, float l1_lambda);
+int desmo_session_upload_snapshot_host(desmo_session* ss, const float* snapshot_host /*[m][n]*/);
+int desmo_session_step_host(desmo_session* ss, const float* snapshot_host_or_null, float* losses_host /*[4]*/);
+int desmo_session_get_params_host(desmo_session* ss, float* phi, float* gates, float* rows_or_coefs, float* periods, float* omega);
+
+/* Reference-facing whole-run entry point with HOST buffers (what the reference's training loop CYL:706-778 does for one
+ * process): uploads snapshot_host[m][n] (fp32, the reference's (m, n) batch), POD modes pod_host[n][r] (fp64, as
+ * POD_analysis returns them) and the packed parameters, runs `steps` fused steps, returns the parameters and the
+ * per-step losses[steps][4].  lrs[5], beta, l1_lambda as in CYL:592-612,700-701. */
+int desmo_train_host(int64_t n, int32_t m, int32_t r, int32_t polyorder, int32_t nF, const float* snapshot_host,
+                     const double* pod_host, float* phi_host /*[r][n]*/, float* gates_host /*[K]*/,
+                     float* rows_or_coefs_host /*[K][m] or [K][2nF+1]*/, float* periods_host /*[K] or NULL*/,
+                     float* omega_host /*[3r]*/, const float* lrs, float beta, float l1_lambda, int32_t steps,
+                     float* losses_host /*[steps][4]*/, int32_t path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DESMO_B200_H */

@@ -1,0 +1,73 @@
+"""CPU-side checks of the boundary: the C-ABI library builds/loads and exports every symbol include/desmo_b200.h declares;
+host logic (scheduler, shapes, error behaviour without a GPU).  No compute calls."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from desmo_b200 import _lib
+from oracle import desmo_oracle as orc
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 20
+    assert set(declared) == set(_lib.SIGNATURES), (set(declared) ^ set(_lib.SIGNATURES))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.desmo_version()
+
+
+def test_library_term_counts_match_reference_facts():
+    lib = _lib.load()
+    for (r, p) in [(4, 3), (4, 2), (2, 2), (3, 4), (2, 7), (8, 1)]:
+        assert lib.desmo_num_terms(r, p) == orc.number_of_terms(r, p)
+        assert lib.desmo_padded_k(r, p) % 16 == 0 and lib.desmo_padded_k(r, p) >= orc.number_of_terms(r, p) + 3 * r
+    assert lib.desmo_num_terms(8, 3) < 0  # K = 189 > DESMO_MAX_K: reported as unsupported, never silently truncated
+    assert lib.desmo_num_terms(2, 8) < 0 and lib.desmo_num_terms(0, 2) < 0
+
+
+def test_shape_validation_and_error_strings():
+    lib = _lib.load()
+    bad = _lib.make_shape(1000, 100, 4, 2, ld=1000)  # pitch not a multiple of 128
+    assert lib.desmo_red_count(ctypes.byref(bad)) == -1
+    assert b"ld=" in lib.desmo_last_error()
+    ok = _lib.make_shape(1000, 100, 4, 2)
+    K, Kp = 27, 32
+    assert lib.desmo_red_count(ctypes.byref(ok)) == Kp * ok.mld + 1 + 16 + 12
+    assert ok.ld % 128 == 0 and ok.mld % 16 == 0
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import desmo_b200
+
+    with pytest.raises(desmo_b200.DesmoError):
+        desmo_b200.DESMO(100, 10, 2, 2)
+    lib = _lib.load()
+    n = ctypes.c_size_t()
+    assert lib.desmo_workspace_bytes(ctypes.byref(_lib.make_shape(1000, 100, 4, 2)), ctypes.byref(n)) == 3  # DESMO_ERR_CUDA
+    out = ctypes.c_void_p()
+    assert lib.desmo_session_create(1000, 100, 4, 2, 0, 0, ctypes.byref(out)) == 3
+
+
+def test_plateau_scheduler_matches_torch():
+    import torch
+
+    from desmo_b200.trainer import PlateauScheduler
+
+    prm = [torch.nn.Parameter(torch.zeros(1)) for _ in range(4)]
+    opt = torch.optim.Adamax([{"params": [p], "lr": lr} for p, lr in zip(prm, (1e-2, 1e-3, 1e-2, 1e3))])
+    ref = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="min", patience=2, factor=0.1, min_lr=1e-6)
+    mine = PlateauScheduler((1e-2, 1e-3, 1e-2, 1e3), patience=2)
+    rng = np.random.default_rng(0)
+    metric = 10.0
+    for it in range(200):
+        metric = metric * (0.9 if it % 17 == 0 else 1.0) + 1e-6 * rng.standard_normal()
+        ref.step(metric)
+        mine.step(metric)
+        assert np.allclose(mine.lrs, [g["lr"] for g in opt.param_groups], rtol=1e-12), it
