@@ -35,7 +35,9 @@ def _check_grads(e, out, beta, lam, tol_scale=1.0):
     torch.cuda.synchronize()
     losses = e.losses.cpu().numpy()
     assert abs(losses[0] - out["mse"]) <= 1e-5 * abs(out["mse"]), (losses[0], out["mse"])
-    assert abs(losses[1] - out["ortho"]) <= 1e-5 * abs(out["ortho"]) + 1e-8
+    # ortho = sum |Phi_i . Phi_j| of nearly orthogonal unit-norm vectors: each dot carries ~1e-7 ABSOLUTE fp32 cancellation
+    # noise in the reference itself, so the gate is 1e-5 relative plus that absolute floor
+    assert abs(losses[1] - out["ortho"]) <= 1e-5 * abs(out["ortho"]) + 1e-6
     assert abs(losses[2] - out["l1"]) <= 1e-6 * abs(out["l1"])
     assert abs(losses[3] - out["total"]) <= 1e-5 * abs(out["total"])
     for k, ref in out["grads"].items():
