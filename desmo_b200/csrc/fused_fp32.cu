@@ -315,6 +315,10 @@ __global__ void reduce_partials_kernel(const float* __restrict__ Epart, int nx, 
     }
 }
 
+void reduce_partials_launch(const float* Epart, int nx, long long ecount, const double* Spart, int nslots, int r, float* red, cudaStream_t st) {
+    reduce_partials_kernel<<<(unsigned)((ecount + 255) / 256), 256, 0, st>>>(Epart, nx, ecount, Spart, nslots, r, red);
+}
+
 template <int KP>
 static int launch_fused(const FusedArgs& a, int sms, size_t smem_cap, cudaStream_t st, int* gx_out, int* nslots_out) {
     using L = FusedSmem<KP>;

@@ -1,4 +1,6 @@
 // Temporal side of the library: rows (free vectors or Fourier series) and W = diag(gates) * rows.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace desmo {
@@ -30,7 +32,8 @@ __device__ __forceinline__ float fourier_value(const float* __restrict__ c, int 
 // grid = Kp blocks (one library term each), 256 threads over time.
 __global__ void build_w_kernel(int K, int m, int mld, int nF, const float* __restrict__ gates, float* __restrict__ rows,
                                const float* __restrict__ coefs, const float* __restrict__ periods, float* __restrict__ W,
-                               float* __restrict__ Whi, float* __restrict__ Wlo, int32_t* step_dev, float* l1_out) {
+                               __nv_bfloat16* __restrict__ Wb, int Kp, int32_t* step_dev, float* l1_out) {
+    // Wb: three bf16 planes [3][32][mld] of W for the tcgen05 path (w = b1 + b2 + b3), rows >= K zero
     const int k = blockIdx.x;
     if (k == 0 && threadIdx.x < 32) {
         float s = 0.0f;
@@ -55,18 +58,25 @@ __global__ void build_w_kernel(int K, int m, int mld, int nF, const float* __res
             }
             w = gate * z;
         }
-        W[(size_t)k * mld + t] = w;
-        if (Whi) {  // TF32 split for the tensor-core path: hi = w with the low 13 mantissa bits cleared, lo = w - hi (exact)
-            const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
-            Whi[(size_t)k * mld + t] = hi;
-            Wlo[(size_t)k * mld + t] = w - hi;
+        if (k < Kp) W[(size_t)k * mld + t] = w;
+        if (Wb && k < 32) {
+            const __nv_bfloat16 b1 = __float2bfloat16_rn(w);
+            const float e1 = w - __bfloat162float(b1);
+            const __nv_bfloat16 b2 = __float2bfloat16_rn(e1);
+            const __nv_bfloat16 b3 = __float2bfloat16_rn(e1 - __bfloat162float(b2));
+            Wb[(size_t)k * mld + t] = b1;
+            Wb[(size_t)(32 + k) * mld + t] = b2;
+            Wb[(size_t)(64 + k) * mld + t] = b3;
         }
     }
 }
 
 int build_w(const desmo_shape* s, int K, int Kp, const float* gates, float* rows, const float* coefs, const float* periods,
             float* W, float* Whi, float* Wlo, int32_t* step_dev, float* l1_out, cudaStream_t st) {
-    build_w_kernel<<<Kp, 256, 0, st>>>(K, s->m, s->mld, s->nF, gates, rows, coefs, periods, W, Whi, Wlo, step_dev, l1_out);
+    (void)Wlo;
+    const int grid = (Whi && Kp < 32) ? 32 : Kp;
+    build_w_kernel<<<grid, 256, 0, st>>>(K, s->m, s->mld, s->nF, gates, rows, coefs, periods, W, reinterpret_cast<__nv_bfloat16*>(Whi), Kp,
+                                         step_dev, l1_out);
     DESMO_CUDA(cudaGetLastError());
     return DESMO_OK;
 }
