@@ -183,7 +183,10 @@ def main():
     from desmo_b200 import DESMO, DesmoTrainer, _lib
 
     n_global = n * world
-    model = DESMO(n, m, p, r, 10000, device=dev, n_global=n_global, path=args.path)
+    import contextlib
+
+    with contextlib.redirect_stdout(sys.stderr):  # the module prints the reference's banner (CYL:510); keep stdout = one JSON line
+        model = DESMO(n, m, p, r, 10000, device=dev, n_global=n_global, path=args.path)
     e = model.engine
     e.U = synth_on_device(torch, n, m, dev, seed=2, x_offset=rank * n, n_global=n_global)
     sigma = e.pod_from_snapshot()  # POD init on the device (method of snapshots)

@@ -259,6 +259,13 @@ int desmo_library_colnorm2(const desmo_shape* s, const float* P, const float* ph
     return launch_colnorm2(a, (cudaStream_t)stream);
 }
 
+int desmo_debug_timers(const desmo_shape* s, void* workspace, uint64_t* out_host, int32_t count) {
+    (void)s; (void)workspace;
+    if (!out_host || count < 1) { set_error("desmo_debug_timers: bad argument"); return DESMO_ERR_ARG; }
+    if (tc_debug_read(out_host, count)) { set_error("desmo_debug_timers: no debug run recorded (set DESMO_TC_DEBUG=1)"); return DESMO_ERR_ARG; }
+    return DESMO_OK;
+}
+
 int desmo_pod_gram(const desmo_shape* s, const float* U, float* C, void* workspace, void* stream) {
     Dims d;
     int rc = validate_shape(s, &d);

@@ -12,6 +12,8 @@
 // (thread <-> mesh point == TMEM lane; warps 4-7 take snapshots 0-63 of the slab, warps 8-11 snapshots 64-127).
 // The MMA issuer runs G1 of slab s+1 ahead of G3/G4 of slab s, so the tensor pipe works while the epilogue forms R.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -25,14 +27,23 @@ constexpr int BT = 128;         // snapshots per slab (MMA N of G1, K of G3, M o
 constexpr int MAXSLAB = 8;      // TMEM: 8 x 32 columns of E accumulators
 constexpr int THREADS = 384;
 constexpr uint32_t R_PLANE = 2 * BP * 128;            // one bf16 plane of R: 2 boxes [128 p rows x 128 B (64 t)]
-constexpr uint32_t W_PLANE = 2 * KP * 128;            // one bf16 plane of a W slab: 2 boxes [32 lib rows x 128 B (64 t)]
+constexpr uint32_t W_BOX = 3 * KP * 128;              // W slab box: [3 planes x 32 lib rows][128 B = 64 t]; planes stacked along rows
+constexpr uint32_t W_PLANE = KP * 128;                // row offset of a plane inside a box
+constexpr uint32_t W_SLAB = 2 * W_BOX;                // two boxes (snapshots 0-63, 64-127)
 constexpr uint32_t G_PLANE = 2 * KP * 128;            // one bf16 plane of G: 2 boxes [32 lib rows x 128 B (64 p)]
 constexpr uint32_t R_OFF = 0;
 constexpr uint32_t W_OFF = R_OFF + 3 * R_PLANE;        // 98304
-constexpr uint32_t G_OFF = W_OFF + 2 * 3 * W_PLANE;    // 147456
-constexpr uint32_t RED_OFF = G_OFF + 3 * G_PLANE;      // 172032  (4 warps x kScal doubles)
+constexpr uint32_t G_OFF = W_OFF + 2 * W_SLAB;         // 147456
+// U staging: each epilogue half (snapshots 0-63 / 64-127 of a slab) owns a private ring of 3 TMA stages of [16 snapshots][128 points]
+// fp32.  Private rings matter: mbarrier parity waits are only sound if a waiter is never two phases away from the barrier, which a
+// ring shared by two independently progressing consumer groups cannot guarantee.
+constexpr uint32_t U_OFF = G_OFF + 3 * G_PLANE;        // 172032
+constexpr int U_ROWS = 16;
+constexpr uint32_t U_STAGE = U_ROWS * BP * 4;          // 8192
+constexpr int U_STAGES = 3;                            // per half
+constexpr uint32_t RED_OFF = U_OFF + 2 * U_STAGES * U_STAGE;  // 221184  (4 warps x kScal doubles)
 constexpr uint32_t SMEM_BYTES = RED_OFF + 4 * kScal * 8 + 1024;  // + alignment slack
-constexpr uint32_t TMEM_REC = 0, TMEM_D = 128, TMEM_E = 256;
+constexpr uint32_t TMEM_REC = 0, TMEM_D = 128, TMEM_E = 256;  // D: 3 column blocks of 32 (N-stacked B planes), summed in the epilogue
 }  // namespace tc
 
 struct TcArgs {
@@ -45,6 +56,7 @@ struct TcArgs {
     double* Spart;
     long long n, ld;
     int m, mld, r, T, K, nslab, kp_out;
+    unsigned long long* dbg;  // optional per-CTA phase timers (cycles), 32 per CTA
     float scale;
     MonoTable mt;
 };
@@ -57,11 +69,28 @@ __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t byte_in_row) {
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ unsigned long long* g_tc_dbg = nullptr;  // host-mapped diagnostics buffer (DESMO_TC_DEBUG), survives a trap
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0, int iter = 0) {
     uint32_t done = 0;
-    while (!done)
+    unsigned spins = 0;
+    while (!done) {
         asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && g_tc_dbg && ++spins >= (1u << 22)) {  // only armed in debug runs: report who is stuck, later abort the grid
+            if (spins == (1u << 22)) {
+                unsigned long long* d = g_tc_dbg + 4096 + (blockIdx.x * 12 + (threadIdx.x >> 5)) * 4;
+                d[0] = 0xdead0000ull | (unsigned)tag; d[1] = (unsigned long long)iter; d[2] = parity; d[3] = threadIdx.x;
+                __threadfence_system();
+            }
+            if (spins > (1u << 24)) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void dbg_mark(int it, int step) {  // debug runs only: last point reached by each warp
+    if (g_tc_dbg && (threadIdx.x & 31) == 0) {
+        volatile unsigned long long* d = g_tc_dbg + 12288 + blockIdx.x * 12 + (threadIdx.x >> 5);
+        *d = ((unsigned long long)it << 8) | (unsigned)step;
+    }
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -100,6 +129,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
                    "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %1;\n\t@px mov.s32 %0, 1;\n\t}\n" : "+r"(pred) : "r"(0xffffffffu));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // x = b1 + b2 + b3 (bf16 each, round-to-nearest): packs two consecutive elements (lo = first) per 32-bit word
@@ -111,20 +151,25 @@ __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t& w1, ui
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w3) : "f"(f1), "f"(f0));
 }
 
-// six (a-plane, b-plane) products kept by the 3-way split, smallest contributions first
-__device__ __constant__ int kPairA[6] = {2, 0, 1, 1, 0, 0};
-__device__ __constant__ int kPairB[6] = {0, 2, 1, 0, 1, 0};
+// The six (a-plane, b-plane) products kept by the 3-way split (i + j <= 4), smallest contributions first.
+// Descriptors: the high word is constant per operand role; the low word is (addr >> 4) | (LBO >> 4) << 16, so stepping through
+// planes / k-steps is ONE 32-bit add of a compile-time constant per operand (smem addresses < 256 KB never carry out of 14 bits).
+#define DESMO_PAIRS(X) X(2, 0) X(0, 2) X(1, 1) X(1, 0) X(0, 1) X(0, 0)
+__device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
 
-__global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmW) {
+__global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmW,
+                                                                          const __grid_constant__ CUtensorMap tmU) {
     using namespace tc;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[16];
+    __shared__ __align__(8) uint64_t bars[32];
     __shared__ uint32_t tmem_base_s;
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     double* red_s = reinterpret_cast<double*>(smem + RED_OFF);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    enum { W_FULL0 = 0, W_FULL1, W_EMPTY0, W_EMPTY1, REC_FULL, REC_EMPTY, R_FULL, R_EMPTY, G_FULL, G_EMPTY, D_FULL, D_EMPTY };
+    enum { W_FULL0 = 0, W_FULL1, W_EMPTY0, W_EMPTY1, REC_FULL, REC_EMPTY, R_FULL, R_EMPTY, G_FULL, G_EMPTY, D_FULL, D_EMPTY,
+           U_FULL0, U_EMPTY0 = U_FULL0 + 6 };  // 2 halves x 3 stages each
     auto bar = [&](int i) { return smem_u32(&bars[i]); };
 
     const int nslab = a.nslab;
@@ -135,7 +180,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
     if (tid == 32) {
         mbar_init(bar(W_FULL0), 1); mbar_init(bar(W_FULL1), 1); mbar_init(bar(W_EMPTY0), 1); mbar_init(bar(W_EMPTY1), 1);
         mbar_init(bar(REC_FULL), 1); mbar_init(bar(REC_EMPTY), 256); mbar_init(bar(R_FULL), 256); mbar_init(bar(R_EMPTY), 1);
-        mbar_init(bar(G_FULL), 128); mbar_init(bar(G_EMPTY), 1); mbar_init(bar(D_FULL), 1); mbar_init(bar(D_EMPTY), 128);
+        mbar_init(bar(G_FULL), 256); mbar_init(bar(G_EMPTY), 1); mbar_init(bar(D_FULL), 1); mbar_init(bar(D_EMPTY), 128);
+        for (int i = 0; i < 2 * U_STAGES; ++i) { mbar_init(bar(U_FULL0 + i), 1); mbar_init(bar(U_EMPTY0 + i), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -150,72 +196,99 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
 
     if (warp == 0) {
         // ================================================ TMA producer: W slab planes ================================================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
             for (int it = 0; it < total; ++it) {
                 const int buf = it & 1, slab = it % nslab;
-                if (it >= 2) mbar_wait(bar(W_EMPTY0 + buf), ((it >> 1) & 1) ^ 1);
-                mbar_expect_tx(bar(W_FULL0 + buf), 3 * W_PLANE);
-                for (int s = 0; s < 3; ++s)
-                    for (int h = 0; h < 2; ++h)
-                        tma_load_2d(sbase + W_OFF + buf * 3 * W_PLANE + s * W_PLANE + h * (KP * 128), &tmW, slab * BT + h * 64, s * KP,
-                                    bar(W_FULL0 + buf));
+                if (it >= 2) mbar_wait(bar(W_EMPTY0 + buf), ((it >> 1) & 1) ^ 1, 1, it);
+                mbar_expect_tx(bar(W_FULL0 + buf), W_SLAB);
+                for (int h = 0; h < 2; ++h)
+                    tma_load_2d(sbase + W_OFF + buf * W_SLAB + h * W_BOX, &tmW, slab * BT + h * 64, 0, bar(W_FULL0 + buf));
+            }
+        }
+    } else if (warp == 3 || warp == 2) {
+        // ================================================ TMA producers: U chunks, one thread per epilogue half ==========
+        if (elect_one_sync()) {
+            const int h = warp - 2;
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmU) : "memory");
+            for (int it = 0; it < total; ++it) {
+                const int slab = it % nslab;
+                const long long tile = blockIdx.x + (long long)(it / nslab) * gridDim.x;
+                for (int k = 0; k < 64 / U_ROWS; ++k) {
+                    const int cnt = it * (64 / U_ROWS) + k, st = h * U_STAGES + cnt % U_STAGES;
+                    if (cnt >= U_STAGES) mbar_wait(bar(U_EMPTY0 + st), ((cnt / U_STAGES) - 1) & 1, 2, cnt);
+                    mbar_expect_tx(bar(U_FULL0 + st), U_STAGE);
+                    tma_load_2d(sbase + U_OFF + st * U_STAGE, &tmU, (int)(tile * BP), slab * BT + h * 64 + k * U_ROWS, bar(U_FULL0 + st));
+                }
             }
         }
     } else if (warp == 1) {
         // ================================================ MMA issuer ================================================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc_g1 = make_idesc_bf16(BP, BT, 1, 1);
-            constexpr uint32_t idesc_g3 = make_idesc_bf16(BP, KP, 0, 0);
             constexpr uint32_t idesc_g4 = make_idesc_bf16(BT, KP, 1, 0);
+            unsigned long long tm[6] = {0, 0, 0, 0, 0, 0};
             auto issue_g1 = [&](int it) {
                 const int buf = it & 1, slab = it % nslab, tl = it / nslab;
-                mbar_wait(bar(W_FULL0 + buf), (it >> 1) & 1);
-                if (it > 0) mbar_wait(bar(REC_EMPTY), (it - 1) & 1);
-                if (slab == 0) mbar_wait(bar(G_FULL), tl & 1);
+                long long c0 = clock64();
+                mbar_wait(bar(W_FULL0 + buf), (it >> 1) & 1, 3, it);
+                long long c1 = clock64(); tm[0] += c1 - c0;
+                if (it > 0) mbar_wait(bar(REC_EMPTY), (it - 1) & 1, 4, it);
+                c0 = clock64(); tm[1] += c0 - c1;
+                if (slab == 0) mbar_wait(bar(G_FULL), tl & 1, 5, it);
+                c1 = clock64(); tm[2] += c1 - c0;
                 tc_fence_after();
-                const uint32_t gb = sbase + G_OFF, wb = sbase + W_OFF + buf * 3 * W_PLANE;
+                // A = G_s MN-major (M = points, 2 boxes LBO = 4096), B = W_s MN-major (N = snapshots, 2 boxes LBO = W_BOX)
+                const uint32_t ga_lo = ((sbase + G_OFF) >> 4) | ((KP * 128u >> 4) << 16);
+                const uint32_t wa_lo = ((sbase + W_OFF + buf * W_SLAB) >> 4) | ((W_BOX >> 4) << 16);
                 uint32_t acc = 0;
-#pragma unroll 1
-                for (int pr = 0; pr < 6; ++pr) {
-                    const uint32_t ga = gb + kPairA[pr] * G_PLANE, wa = wb + kPairB[pr] * W_PLANE;
-#pragma unroll
-                    for (int ks = 0; ks < KP / 16; ++ks) {
-                        mma_bf16(tmem + TMEM_REC, make_desc(ga + ks * 2048, KP * 128, 1024), make_desc(wa + ks * 2048, KP * 128, 1024),
-                                 idesc_g1, acc);
-                        acc = 1;
-                    }
-                }
+#define G1_PAIR(PA, PB)                                                                                              \
+    _Pragma("unroll") for (int ks = 0; ks < KP / 16; ++ks) {                                                          \
+        mma_bf16(tmem + TMEM_REC, desc_from(ga_lo + ((PA * G_PLANE + ks * 2048) >> 4), kDescHi),                      \
+                 desc_from(wa_lo + ((PB * W_PLANE + ks * 2048) >> 4), kDescHi), idesc_g1, acc);                       \
+        acc = 1;                                                                                                      \
+    }
+                DESMO_PAIRS(G1_PAIR)
+#undef G1_PAIR
                 umma_commit(bar(REC_FULL));
             };
             auto issue_g34 = [&](int it) {
                 const int buf = it & 1, slab = it % nslab, tl = it / nslab;
-                mbar_wait(bar(R_FULL), it & 1);
-                if (slab == 0 && tl > 0) mbar_wait(bar(D_EMPTY), (tl - 1) & 1);
+                long long c0 = clock64();
+                mbar_wait(bar(R_FULL), it & 1, 6, it);
+                long long c1 = clock64(); tm[3] += c1 - c0;
+                if (slab == 0 && tl > 0) mbar_wait(bar(D_EMPTY), (tl - 1) & 1, 7, it);
+                c0 = clock64(); tm[4] += c0 - c1;
                 tc_fence_after();
-                const uint32_t rb = sbase + R_OFF, wb = sbase + W_OFF + buf * 3 * W_PLANE, gb = sbase + G_OFF;
+                const uint32_t rk_lo = ((sbase + R_OFF) >> 4) | (1u << 16);                       // R_s K-major (G3 A)
+                const uint32_t rm_lo = ((sbase + R_OFF) >> 4) | ((BP * 128u >> 4) << 16);         // R_s MN-major (G4 A), LBO = 16384
+                const uint32_t wk_lo = ((sbase + W_OFF + buf * W_SLAB) >> 4) | (1u << 16);        // W_s K-major (G3 B)
+                const uint32_t gk_lo = ((sbase + G_OFF) >> 4) | (1u << 16);                       // G_s K-major (G4 B)
                 uint32_t acc = slab > 0 ? 1u : 0u;
-#pragma unroll 1
-                for (int pr = 0; pr < 6; ++pr) {  // G3: D += R W^T   (A = R K-major, B = W K-major, K = snapshots)
-                    const uint32_t ra = rb + kPairA[pr] * R_PLANE, wa = wb + kPairB[pr] * W_PLANE;
-#pragma unroll
-                    for (int ks = 0; ks < BT / 16; ++ks) {
-                        mma_bf16(tmem + TMEM_D, make_desc(ra + (ks >> 2) * (BP * 128) + (ks & 3) * 32, 16, 1024),
-                                 make_desc(wa + (ks >> 2) * (KP * 128) + (ks & 3) * 32, 16, 1024), idesc_g3, acc);
-                        acc = 1;
-                    }
-                }
+                // G3: D += R W^T   (K = snapshots: 8 k-steps of 16; box = ks / 4, 32 B per k-step inside the swizzled row).
+                // The B planes are stacked along N: plane a of R multiplies planes 0..2-a of W in ONE MMA of N = 32*(3-a); column
+                // block b of D then holds sum_a R_a W_b and the three blocks are added when D is read (A is fetched 3x, not 6x).
+#define G3_PLANE(PA)                                                                                                 \
+    _Pragma("unroll") for (int ks = 0; ks < BT / 16; ++ks) {                                                          \
+        mma_bf16(tmem + TMEM_D, desc_from(rk_lo + ((PA * R_PLANE + (ks >> 2) * (BP * 128) + (ks & 3) * 32) >> 4), kDescHi), \
+                 desc_from(wk_lo + (((ks >> 2) * W_BOX + (ks & 3) * 32) >> 4), kDescHi), make_idesc_bf16(BP, KP * (3 - PA), 0, 0), \
+                 (PA == 0) ? acc0 : 1u);                                                                              \
+        if (PA == 0) acc0 = 1;                                                                                        \
+    }
+                uint32_t acc0 = acc;
+                G3_PLANE(0) G3_PLANE(1) G3_PLANE(2)
+#undef G3_PLANE
                 acc = tl > 0 ? 1u : 0u;
-#pragma unroll 1
-                for (int pr = 0; pr < 6; ++pr) {  // G4: E^T += R^T G  (A = R MN-major, B = G K-major, K = points)
-                    const uint32_t ra = rb + kPairA[pr] * R_PLANE, ga = gb + kPairB[pr] * G_PLANE;
-#pragma unroll
-                    for (int ks = 0; ks < BP / 16; ++ks) {
-                        mma_bf16(tmem + TMEM_E + slab * KP, make_desc(ra + ks * 2048, BP * 128, 1024),
-                                 make_desc(ga + (ks >> 2) * (KP * 128) + (ks & 3) * 32, 16, 1024), idesc_g4, acc);
-                        acc = 1;
-                    }
-                }
+                const uint32_t e_tmem = tmem + TMEM_E + slab * KP;
+                // G4: E^T += R^T G  (K = points: 8 k-steps of 16 rows = 2048 B; B = G_s K-major, box = ks / 4)
+#define G4_PAIR(PA, PB)                                                                                              \
+    _Pragma("unroll") for (int ks = 0; ks < BP / 16; ++ks) {                                                          \
+        mma_bf16(e_tmem, desc_from(rm_lo + ((PA * R_PLANE + ks * 2048) >> 4), kDescHi),                                \
+                 desc_from(gk_lo + ((PB * G_PLANE + (ks >> 2) * (KP * 128) + (ks & 3) * 32) >> 4), kDescHi), idesc_g4, acc); \
+        acc = 1;                                                                                                      \
+    }
+                DESMO_PAIRS(G4_PAIR)
+#undef G4_PAIR
                 umma_commit(bar(R_EMPTY));
                 umma_commit(bar(W_EMPTY0 + buf));
                 if (slab == nslab - 1) {
@@ -230,6 +303,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 issue_g34(it);
                 if (!next_same_tile && it + 1 < total) issue_g1(it + 1);  // new tile: its G needs G4 of the old tile finished
             }
+            if (a.dbg) for (int i = 0; i < 5; ++i) a.dbg[blockIdx.x * 32 + i] = tm[i];
         }
     } else if (warp >= 4) {
         // ================================================ epilogue warps ================================================
@@ -238,21 +312,25 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         double loss_acc = 0.0;
         float lat[kMaxR], dl[tc::KP], dph[kMaxR], dom[3 * kMaxR];
+        unsigned long long te[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const long long tstart = clock64();
 
         auto chain_and_store = [&](int tile_local, long long tile) {
             // D of the finished tile -> d mse/d phi, d omega, Phi^T Phi   (warps 8..11)
             const long long x = tile * BP + p;
-            mbar_wait(bar(D_FULL), tile_local & 1);
+            mbar_wait(bar(D_FULL), tile_local & 1, 8, tile_local);
             tc_fence_after();
-            uint32_t v[16];
-            tmem_ld16(tmem + lane_addr + TMEM_D, v);
-            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dl[j] = __uint_as_float(v[j]) * a.scale;
-            tmem_ld16(tmem + lane_addr + TMEM_D + 16, v);
-            tmem_ld_wait();
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v0[16], v1[16], v2[16];
+                tmem_ld16(tmem + lane_addr + TMEM_D + c * 16, v0);
+                tmem_ld16(tmem + lane_addr + TMEM_D + KP + c * 16, v1);
+                tmem_ld16(tmem + lane_addr + TMEM_D + 2 * KP + c * 16, v2);
+                tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dl[16 + j] = __uint_as_float(v[j]) * a.scale;
+                for (int j = 0; j < 16; ++j)
+                    dl[c * 16 + j] = ((__uint_as_float(v2[j]) + __uint_as_float(v1[j])) + __uint_as_float(v0[j])) * a.scale;
+            }
             tc_fence_before();
             mbar_arrive(bar(D_EMPTY));
             for (int i = 0; i < a.r; ++i) lat[i] = a.phi[(long long)i * a.ld + x] * a.P[(long long)i * a.ld + x];
@@ -275,12 +353,19 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             const long long tile = blockIdx.x + (long long)tl * gridDim.x;
             const long long x = tile * BP + p;
             const bool xin = x < a.n;
-            if (h == 0) {
-                // ---- library row of this point (CYL:538-548,565-567), split into bf16 planes, G_s[lib rows][p contiguous] ----
+            long long cg0 = clock64();
+            {
+                // ---- library row of this point (CYL:538-548,565-567), split into bf16 planes, G_s[lib rows][p contiguous].
+                //      Both halves of the epilogue share the work (h takes library terms j = h, h+2, ...).  Rolled loops on
+                //      purpose: this runs once per tile, and straight-line code here only thrashes the I-cache. ----
                 for (int i = 0; i < a.r; ++i) lat[i] = a.phi[(long long)i * a.ld + x] * a.P[(long long)i * a.ld + x];
-                float g[KP];
-#pragma unroll
-                for (int j = 0; j < KP; ++j) {
+                long long cg1 = clock64();
+                if (tl > 0) mbar_wait(bar(G_EMPTY), (tl - 1) & 1, 9, tl);
+                cg0 = clock64(); te[5] += cg0 - cg1;
+                const uint32_t gs = sbase + G_OFF + (p >> 6) * (KP * 128);
+                const uint32_t pb = (p & 63) * 2;
+#pragma unroll 1
+                for (int j = h; j < KP; j += 2) {
                     float v = 0.0f;
                     if (j < a.T) {
                         v = monomial(a.mt, j, lat, 1);
@@ -289,75 +374,78 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                         const float arg = a.omega[3 * i + b] * lat[i];
                         v = (b == 0) ? sinf(arg) : (b == 1) ? cosf(arg) : tanhf(arg);
                     }
-                    g[j] = v;
-                }
-                if (tl > 0) mbar_wait(bar(G_EMPTY), (tl - 1) & 1);
-                uint8_t* gs = smem + G_OFF + (p >> 6) * (KP * 128);
-                const uint32_t pb = (p & 63) * 2;
-#pragma unroll
-                for (int j = 0; j < KP; ++j) {
-                    const __nv_bfloat16 b1 = __float2bfloat16_rn(g[j]);
-                    const float e1 = g[j] - __bfloat162float(b1);
+                    const __nv_bfloat16 b1 = __float2bfloat16_rn(v);
+                    const float e1 = v - __bfloat162float(b1);
                     const __nv_bfloat16 b2 = __float2bfloat16_rn(e1);
                     const __nv_bfloat16 b3 = __float2bfloat16_rn(e1 - __bfloat162float(b2));
                     const uint32_t off = sw128(j, pb);
-                    *reinterpret_cast<__nv_bfloat16*>(gs + off) = b1;
-                    *reinterpret_cast<__nv_bfloat16*>(gs + G_PLANE + off) = b2;
-                    *reinterpret_cast<__nv_bfloat16*>(gs + 2 * G_PLANE + off) = b3;
+                    st_shared_u16(gs + off, __bfloat16_as_ushort(b1));
+                    st_shared_u16(gs + G_PLANE + off, __bfloat16_as_ushort(b2));
+                    st_shared_u16(gs + 2 * G_PLANE + off, __bfloat16_as_ushort(b3));
                 }
                 fence_async_smem();
                 mbar_arrive(bar(G_FULL));
-            } else if (tl > 0) {
-                chain_and_store(tl - 1, tile - gridDim.x);
+                te[6] += clock64() - cg0;
             }
+            if (h == 1 && tl > 0) chain_and_store(tl - 1, tile - gridDim.x);
 
+            float u[64];
             for (int slab = 0; slab < nslab; ++slab, ++it) {
                 const int t0 = slab * BT + h * 64;
-                float u[64];
-#pragma unroll
-                for (int j = 0; j < 64; ++j) {
-                    const int t = t0 + j;
-                    u[j] = (xin && t < a.m) ? __ldg(a.U + (long long)t * a.ld + x) : 0.0f;
-                }
-                mbar_wait(bar(REC_FULL), it & 1);
+                long long c0 = clock64();
+                mbar_wait(bar(REC_FULL), it & 1, 10, it);
+                long long c1 = clock64(); te[0] += c1 - c0;
                 tc_fence_after();
                 float lsum = 0.0f;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v[16];
-                    tmem_ld16(tmem + lane_addr + TMEM_REC + h * 64 + c * 16, v);
+                for (int k = 0; k < 64 / U_ROWS; ++k) {
+                    const int cnt = it * (64 / U_ROWS) + k, st = h * U_STAGES + cnt % U_STAGES;
+                    uint32_t v0[16];
+                    tmem_ld16(tmem + lane_addr + TMEM_REC + h * 64 + k * 16, v0);
+                    mbar_wait(bar(U_FULL0 + st), (cnt / U_STAGES) & 1, 11, cnt);
+                    const uint32_t us = sbase + U_OFF + st * U_STAGE + p * 4;
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int t = t0 + c * 16 + j;
-                        const float rr = (xin && t < a.m) ? __uint_as_float(v[j]) - u[c * 16 + j] : 0.0f;
-                        u[c * 16 + j] = rr;
+                        const int t = t0 + k * 16 + j;
+                        float uv;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(uv) : "r"(us + j * (BP * 4)));
+                        const float rr = (xin && t < a.m) ? __uint_as_float(v0[j]) - uv : 0.0f;
+                        u[k * 16 + j] = rr;
                         lsum = fmaf(rr, rr, lsum);
                     }
+                    mbar_arrive(bar(U_EMPTY0 + st));
                 }
                 loss_acc += (double)lsum;
                 tc_fence_before();
                 mbar_arrive(bar(REC_EMPTY));
-                if (it > 0) mbar_wait(bar(R_EMPTY), (it - 1) & 1);
+                c0 = clock64(); te[1] += c0 - c1;
+                if (it > 0) mbar_wait(bar(R_EMPTY), (it - 1) & 1, 12, it);
+                c1 = clock64(); te[2] += c1 - c0;
                 // ---- r -> three bf16 planes, own row p of box h (64 snapshots = 128 B = 8 chunks of 16 B) ----
-                uint8_t* rs = smem + R_OFF + h * (BP * 128) + p * 128;
+                const uint32_t rs = sbase + R_OFF + h * (BP * 128) + p * 128;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     uint32_t w1[4], w2[4], w3[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) split3_pair(u[c * 8 + 2 * e], u[c * 8 + 2 * e + 1], w1[e], w2[e], w3[e]);
                     const uint32_t off = ((uint32_t)(c ^ (p & 7))) << 4;
-                    *reinterpret_cast<uint4*>(rs + off) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
-                    *reinterpret_cast<uint4*>(rs + R_PLANE + off) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
-                    *reinterpret_cast<uint4*>(rs + 2 * R_PLANE + off) = make_uint4(w3[0], w3[1], w3[2], w3[3]);
+                    st_shared_v4(rs + off, w1[0], w1[1], w1[2], w1[3]);
+                    st_shared_v4(rs + R_PLANE + off, w2[0], w2[1], w2[2], w2[3]);
+                    st_shared_v4(rs + 2 * R_PLANE + off, w3[0], w3[1], w3[2], w3[3]);
                 }
                 fence_async_smem();
                 mbar_arrive(bar(R_FULL));
+                te[3] += clock64() - c1;
             }
+        }
+        if (a.dbg && tid == 128) {
+            for (int i = 0; i < 8; ++i) a.dbg[blockIdx.x * 32 + 8 + i] = te[i];
+            a.dbg[blockIdx.x * 32 + 16] = clock64() - tstart;
         }
         // last tile's chain rule, then the E accumulators of this CTA
         if (h == 1 && my_tiles > 0) chain_and_store(my_tiles - 1, blockIdx.x + (long long)(my_tiles - 1) * gridDim.x);
-        if (total > 0) mbar_wait(bar(R_EMPTY), (total - 1) & 1);
+        if (total > 0) mbar_wait(bar(R_EMPTY), (total - 1) & 1, 13, total);
         tc_fence_after();
         float* Eo = a.Epart + (long long)blockIdx.x * a.kp_out * a.mld;
         for (int slab = h; slab < nslab; slab += 2) {
@@ -391,6 +479,14 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
 }
 
 // ------------------------------------------------------------------------------------------------- host side
+static unsigned long long* g_dbg_host = nullptr;
+constexpr size_t kDbgWords = 16384;
+int tc_debug_read(uint64_t* out, int count) {
+    if (!g_dbg_host) return DESMO_ERR_ARG;
+    memcpy(out, g_dbg_host, sizeof(uint64_t) * (count < (int)kDbgWords ? count : (int)kDbgWords));
+    return DESMO_OK;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
@@ -425,22 +521,42 @@ int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const flo
     CUtensorMap tm;
     const cuuint64_t dims[2] = {(cuuint64_t)s->mld, (cuuint64_t)(3 * tc::KP)};
     const cuuint64_t strides[1] = {(cuuint64_t)s->mld * 2};
-    const cuuint32_t box[2] = {64, (cuuint32_t)tc::KP};
+    const cuuint32_t box[2] = {64, (cuuint32_t)(3 * tc::KP)};  // one box = all three planes of 64 snapshots
     const cuuint32_t estr[2] = {1, 1};
     CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ws.tc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return DESMO_ERR_CUDA; }
+    CUtensorMap tmu;
+    {
+        const cuuint64_t udims[2] = {(cuuint64_t)s->ld, (cuuint64_t)s->m};
+        const cuuint64_t ustr[1] = {(cuuint64_t)s->ld * 4};
+        const cuuint32_t ubox[2] = {(cuuint32_t)tc::BP, (cuuint32_t)tc::U_ROWS};
+        cr = enc(&tmu, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)U, udims, ustr, ubox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(U) failed (%d)", (int)cr); return DESMO_ERR_CUDA; }
+    }
     TcArgs a{};
     a.U = U; a.P = P; a.phi = phi; a.omega = omega; a.dphi = dphi; a.Epart = ws.Epart; a.Spart = ws.Spart;
     a.n = s->n; a.ld = s->ld; a.m = s->m; a.mld = s->mld; a.r = s->r; a.T = T; a.K = T + 3 * s->r;
     a.nslab = (s->m + tc::BT - 1) / tc::BT;
+    a.dbg = nullptr;
+    if (getenv("DESMO_TC_DEBUG")) {
+        unsigned long long* dev = nullptr;
+        if (!g_dbg_host) {
+            DESMO_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_dbg_host), kDbgWords * 8, cudaHostAllocMapped));
+            memset(g_dbg_host, 0, kDbgWords * 8);
+        }
+        DESMO_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev), g_dbg_host, 0));
+        DESMO_CUDA(cudaMemcpyToSymbolAsync(g_tc_dbg, &dev, sizeof(dev), 0, cudaMemcpyHostToDevice, st));
+        a.dbg = dev;
+    }
     a.kp_out = Kp;
     a.scale = (float)(2.0 / ((double)s->n_global * (double)s->m));
     a.mt = mt;
     const long long ntiles = s->ld / tc::BP;
     const int grid = (int)(ntiles < sms ? ntiles : sms);
     DESMO_CUDA(cudaFuncSetAttribute(fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-    fused_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, tm);
+    fused_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, tm, tmu);
     DESMO_CUDA(cudaGetLastError());
     reduce_partials_launch(ws.Epart, grid, (long long)Kp * s->mld, ws.Spart, grid, s->r, red, st);
     DESMO_CUDA(cudaGetLastError());

@@ -118,6 +118,10 @@ int desmo_reconstruct(const desmo_shape* s, const float* P, const float* phi, co
 int desmo_library_colnorm2(const desmo_shape* s, const float* P, const float* phi, const float* omega, float* out_k,
                            void* stream);
 
+/* Diagnostics: per-CTA phase timers (cycles) of the tcgen05 fused kernel, recorded when DESMO_TC_DEBUG is set in the
+ * environment; 16 counters per CTA.  Synchronous. */
+int desmo_debug_timers(const desmo_shape* s, void* workspace, uint64_t* out_host, int32_t count);
+
 /* POD by the method of snapshots (replaces np.linalg.svd, CYL:197-205):
  *   gram    C[m][m] = U U^T  (local partial, TF32x3 tensor-core tiles)      -- all-reduce it across ranks
  *   eig     top-r eigenpairs of C (replicated, on device): sigma[r] = sqrt(lambda), V[r][m]

@@ -1,0 +1,27 @@
+"""Prints the per-phase cycle counters of the tcgen05 fused kernel (DESMO_TC_DEBUG=1)."""
+import ctypes, os, sys
+os.environ["DESMO_TC_DEBUG"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from desmo_b200 import DesmoEngine, _lib
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 128 * 8
+e = DesmoEngine(n, 1000, 2, 4, omega_init=10.0, device=torch.device("cuda:0"), path=2)
+g = torch.Generator(device="cuda").manual_seed(0)
+e.P[:, :n] = torch.randn(4, n, device="cuda", generator=g) / n ** 0.5
+e.U = torch.randn(1000, e.ld, device="cuda", generator=g)
+e.build_w(False)
+for _ in range(3):
+    e.fused_residual_grad()
+torch.cuda.synchronize()
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ev0.record(); e.fused_residual_grad(); ev1.record(); torch.cuda.synchronize()
+print("kernel+reduce ms", ev0.elapsed_time(ev1), "tiles/CTA", n / 128 / 148)
+out = np.zeros(148 * 32, np.uint64)
+_lib.check(e.lib.desmo_debug_timers(ctypes.byref(e.shape), e.workspace.data_ptr(), out.ctypes.data_as(ctypes.c_void_p), out.size))
+t = out.reshape(148, 32).astype(np.float64)
+nst = n / 128 / 148 * 8
+names = ["mma:wait W_FULL", "mma:wait REC_EMPTY", "mma:wait G_FULL", "mma:wait R_FULL", "mma:wait D_EMPTY", "", "", "",
+         "epi:wait REC_FULL", "epi:phase A", "epi:wait R_EMPTY", "epi:phase B", "", "epi:wait G_EMPTY", "epi:G compute+store", "", "epi:total"]
+for i, nm in enumerate(names):
+    if nm:
+        print(f"{nm:22s} mean {t[:, i].mean() / nst:9.0f} cycles/slab-tile   (min {t[:, i].min() / nst:8.0f}, max {t[:, i].max() / nst:8.0f})")
