@@ -25,7 +25,11 @@ constexpr int KP = 32;          // padded library size handled by this kernel
 constexpr int BP = 128;         // points per tile  (MMA M of G1/G3, K of G4)
 constexpr int BT = 128;         // snapshots per slab (MMA N of G1, K of G3, M of G4)
 constexpr int MAXSLAB = 8;      // TMEM: 8 x 32 columns of E accumulators
-constexpr int THREADS = 384;
+constexpr int EPI_WARPS = 16;      // 4 lane quadrants x 4 snapshot quarters
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = 128 + EPI_THREADS;
+constexpr int NQ = 4;              // snapshot quarters per slab
+constexpr int QT = BT / NQ;        // 32 snapshots per epilogue thread
 constexpr uint32_t R_PLANE = 2 * BP * 128;            // one bf16 plane of R: 2 boxes [128 p rows x 128 B (64 t)]
 constexpr uint32_t W_BOX = 3 * KP * 128;              // W slab box: [3 planes x 32 lib rows][128 B = 64 t]; planes stacked along rows
 constexpr uint32_t W_PLANE = KP * 128;                // row offset of a plane inside a box
@@ -34,14 +38,14 @@ constexpr uint32_t G_PLANE = 2 * KP * 128;            // one bf16 plane of G: 2 
 constexpr uint32_t R_OFF = 0;
 constexpr uint32_t W_OFF = R_OFF + 3 * R_PLANE;        // 98304
 constexpr uint32_t G_OFF = W_OFF + 2 * W_SLAB;         // 147456
-// U staging: each epilogue half (snapshots 0-63 / 64-127 of a slab) owns a private ring of 3 TMA stages of [16 snapshots][128 points]
-// fp32.  Private rings matter: mbarrier parity waits are only sound if a waiter is never two phases away from the barrier, which a
-// ring shared by two independently progressing consumer groups cannot guarantee.
+// U staging: each snapshot quarter of the epilogue owns a private ring of 3 TMA stages of [8 snapshots][128 points] fp32.
+// Private rings matter: mbarrier parity waits are only sound if a waiter is never two phases away from the barrier, which a
+// ring shared by independently progressing consumer groups cannot guarantee.
 constexpr uint32_t U_OFF = G_OFF + 3 * G_PLANE;        // 172032
-constexpr int U_ROWS = 16;
-constexpr uint32_t U_STAGE = U_ROWS * BP * 4;          // 8192
-constexpr int U_STAGES = 3;                            // per half
-constexpr uint32_t RED_OFF = U_OFF + 2 * U_STAGES * U_STAGE;  // 221184  (4 warps x kScal doubles)
+constexpr int U_ROWS = 8;
+constexpr uint32_t U_STAGE = U_ROWS * BP * 4;          // 4096
+constexpr int U_STAGES = 3;                            // per quarter
+constexpr uint32_t RED_OFF = U_OFF + NQ * U_STAGES * U_STAGE;  // 221184  (4 quadrants x kScal doubles)
 constexpr uint32_t SMEM_BYTES = RED_OFF + 4 * kScal * 8 + 1024;  // + alignment slack
 constexpr uint32_t TMEM_REC = 0, TMEM_D = 128, TMEM_E = 256;  // D: 3 column blocks of 32 (N-stacked B planes), summed in the epilogue
 }  // namespace tc
@@ -162,14 +166,14 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                                                                           const __grid_constant__ CUtensorMap tmU) {
     using namespace tc;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[32];
+    __shared__ __align__(8) uint64_t bars[40];
     __shared__ uint32_t tmem_base_s;
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     double* red_s = reinterpret_cast<double*>(smem + RED_OFF);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     enum { W_FULL0 = 0, W_FULL1, W_EMPTY0, W_EMPTY1, REC_FULL, REC_EMPTY, R_FULL, R_EMPTY, G_FULL, G_EMPTY, D_FULL, D_EMPTY,
-           U_FULL0, U_EMPTY0 = U_FULL0 + 6 };  // 2 halves x 3 stages each
+           U_FULL0, U_EMPTY0 = U_FULL0 + NQ * U_STAGES };
     auto bar = [&](int i) { return smem_u32(&bars[i]); };
 
     const int nslab = a.nslab;
@@ -179,9 +183,9 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
 
     if (tid == 32) {
         mbar_init(bar(W_FULL0), 1); mbar_init(bar(W_FULL1), 1); mbar_init(bar(W_EMPTY0), 1); mbar_init(bar(W_EMPTY1), 1);
-        mbar_init(bar(REC_FULL), 1); mbar_init(bar(REC_EMPTY), 256); mbar_init(bar(R_FULL), 256); mbar_init(bar(R_EMPTY), 1);
-        mbar_init(bar(G_FULL), 256); mbar_init(bar(G_EMPTY), 1); mbar_init(bar(D_FULL), 1); mbar_init(bar(D_EMPTY), 128);
-        for (int i = 0; i < 2 * U_STAGES; ++i) { mbar_init(bar(U_FULL0 + i), 1); mbar_init(bar(U_EMPTY0 + i), 128); }
+        mbar_init(bar(REC_FULL), 1); mbar_init(bar(REC_EMPTY), EPI_THREADS); mbar_init(bar(R_FULL), EPI_THREADS); mbar_init(bar(R_EMPTY), 1);
+        mbar_init(bar(G_FULL), EPI_THREADS); mbar_init(bar(G_EMPTY), 1); mbar_init(bar(D_FULL), 1); mbar_init(bar(D_EMPTY), 128);
+        for (int i = 0; i < NQ * U_STAGES; ++i) { mbar_init(bar(U_FULL0 + i), 1); mbar_init(bar(U_EMPTY0 + i), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -207,19 +211,20 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             }
         }
     } else if (warp == 3 || warp == 2) {
-        // ================================================ TMA producers: U chunks, one thread per epilogue half ==========
+        // ================= TMA producers: U chunks [8 snapshots][128 points]; each thread feeds the private rings of two quarters ==========
         if (elect_one_sync()) {
-            const int h = warp - 2;
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmU) : "memory");
             for (int it = 0; it < total; ++it) {
                 const int slab = it % nslab;
                 const long long tile = blockIdx.x + (long long)(it / nslab) * gridDim.x;
-                for (int k = 0; k < 64 / U_ROWS; ++k) {
-                    const int cnt = it * (64 / U_ROWS) + k, st = h * U_STAGES + cnt % U_STAGES;
-                    if (cnt >= U_STAGES) mbar_wait(bar(U_EMPTY0 + st), ((cnt / U_STAGES) - 1) & 1, 2, cnt);
-                    mbar_expect_tx(bar(U_FULL0 + st), U_STAGE);
-                    tma_load_2d(sbase + U_OFF + st * U_STAGE, &tmU, (int)(tile * BP), slab * BT + h * 64 + k * U_ROWS, bar(U_FULL0 + st));
-                }
+                for (int k = 0; k < QT / U_ROWS; ++k)
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int h = (warp - 2) * 2 + hh;
+                        const int cnt = it * (QT / U_ROWS) + k, st = h * U_STAGES + cnt % U_STAGES;
+                        if (cnt >= U_STAGES) mbar_wait(bar(U_EMPTY0 + st), ((cnt / U_STAGES) - 1) & 1, 2, cnt);
+                        mbar_expect_tx(bar(U_FULL0 + st), U_STAGE);
+                        tma_load_2d(sbase + U_OFF + st * U_STAGE, &tmU, (int)(tile * BP), slab * BT + h * QT + k * U_ROWS, bar(U_FULL0 + st));
+                    }
             }
         }
     } else if (warp == 1) {
@@ -264,10 +269,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 const uint32_t rm_lo = ((sbase + R_OFF) >> 4) | ((BP * 128u >> 4) << 16);         // R_s MN-major (G4 A), LBO = 16384
                 const uint32_t wk_lo = ((sbase + W_OFF + buf * W_SLAB) >> 4) | (1u << 16);        // W_s K-major (G3 B)
                 const uint32_t gk_lo = ((sbase + G_OFF) >> 4) | (1u << 16);                       // G_s K-major (G4 B)
-                uint32_t acc = slab > 0 ? 1u : 0u;
                 // G3: D += R W^T   (K = snapshots: 8 k-steps of 16; box = ks / 4, 32 B per k-step inside the swizzled row).
                 // The B planes are stacked along N: plane a of R multiplies planes 0..2-a of W in ONE MMA of N = 32*(3-a); column
                 // block b of D then holds sum_a R_a W_b and the three blocks are added when D is read (A is fetched 3x, not 6x).
+                uint32_t acc0 = slab > 0 ? 1u : 0u;
 #define G3_PLANE(PA)                                                                                                 \
     _Pragma("unroll") for (int ks = 0; ks < BT / 16; ++ks) {                                                          \
         mma_bf16(tmem + TMEM_D, desc_from(rk_lo + ((PA * R_PLANE + (ks >> 2) * (BP * 128) + (ks & 3) * 32) >> 4), kDescHi), \
@@ -275,10 +280,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                  (PA == 0) ? acc0 : 1u);                                                                              \
         if (PA == 0) acc0 = 1;                                                                                        \
     }
-                uint32_t acc0 = acc;
                 G3_PLANE(0) G3_PLANE(1) G3_PLANE(2)
 #undef G3_PLANE
-                acc = tl > 0 ? 1u : 0u;
+                umma_commit(bar(W_EMPTY0 + buf));  // W slab is dead after G3: let the producer refill it while G4 runs
+                uint32_t acc = tl > 0 ? 1u : 0u;
                 const uint32_t e_tmem = tmem + TMEM_E + slab * KP;
                 // G4: E^T += R^T G  (K = points: 8 k-steps of 16 rows = 2048 B; B = G_s K-major, box = ks / 4)
 #define G4_PAIR(PA, PB)                                                                                              \
@@ -290,7 +295,6 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 DESMO_PAIRS(G4_PAIR)
 #undef G4_PAIR
                 umma_commit(bar(R_EMPTY));
-                umma_commit(bar(W_EMPTY0 + buf));
                 if (slab == nslab - 1) {
                     umma_commit(bar(D_FULL));
                     umma_commit(bar(G_EMPTY));
@@ -307,16 +311,18 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         }
     } else if (warp >= 4) {
         // ================================================ epilogue warps ================================================
-        const int q = warp & 3, h = (warp - 4) >> 2;
+        // thread <-> (mesh point p == TMEM lane, quarter h of the slab's snapshots): 16 warps, q = lane quadrant, h = snapshots 32h..32h+31
+        const int e = warp - 4, q = e & 3, h = e >> 2;
         const int p = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         double loss_acc = 0.0;
-        float lat[kMaxR], dl[tc::KP], dph[kMaxR], dom[3 * kMaxR];
+        float lat[kMaxR];
         unsigned long long te[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const long long tstart = clock64();
 
         auto chain_and_store = [&](int tile_local, long long tile) {
-            // D of the finished tile -> d mse/d phi, d omega, Phi^T Phi   (warps 8..11)
+            // D of the finished tile -> d mse/d phi, d omega, Phi^T Phi   (warps of quarter 3)
+            float dl[tc::KP], dph[kMaxR], dom[3 * kMaxR];
             const long long x = tile * BP + p;
             mbar_wait(bar(D_FULL), tile_local & 1, 8, tile_local);
             tc_fence_after();
@@ -356,8 +362,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             long long cg0 = clock64();
             {
                 // ---- library row of this point (CYL:538-548,565-567), split into bf16 planes, G_s[lib rows][p contiguous].
-                //      Both halves of the epilogue share the work (h takes library terms j = h, h+2, ...).  Rolled loops on
-                //      purpose: this runs once per tile, and straight-line code here only thrashes the I-cache. ----
+                //      The four quarters share the work (quarter h takes library terms j = h, h+4, ...).  Rolled loops on purpose:
+                //      this runs once per tile, and straight-line code here only thrashes the I-cache. ----
                 for (int i = 0; i < a.r; ++i) lat[i] = a.phi[(long long)i * a.ld + x] * a.P[(long long)i * a.ld + x];
                 long long cg1 = clock64();
                 if (tl > 0) mbar_wait(bar(G_EMPTY), (tl - 1) & 1, 9, tl);
@@ -365,7 +371,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 const uint32_t gs = sbase + G_OFF + (p >> 6) * (KP * 128);
                 const uint32_t pb = (p & 63) * 2;
 #pragma unroll 1
-                for (int j = h; j < KP; j += 2) {
+                for (int j = h; j < KP; j += NQ) {
                     float v = 0.0f;
                     if (j < a.T) {
                         v = monomial(a.mt, j, lat, 1);
@@ -387,31 +393,31 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 mbar_arrive(bar(G_FULL));
                 te[6] += clock64() - cg0;
             }
-            if (h == 1 && tl > 0) chain_and_store(tl - 1, tile - gridDim.x);
+            if (h == NQ - 1 && tl > 0) chain_and_store(tl - 1, tile - gridDim.x);
 
-            float u[64];
             for (int slab = 0; slab < nslab; ++slab, ++it) {
-                const int t0 = slab * BT + h * 64;
+                const int t0 = slab * BT + h * QT;
                 long long c0 = clock64();
                 mbar_wait(bar(REC_FULL), it & 1, 10, it);
                 long long c1 = clock64(); te[0] += c1 - c0;
                 tc_fence_after();
+                uint32_t u[QT];  // Rec of this thread's 32 snapshots, then r = Rec - U in place
+                tmem_ld16(tmem + lane_addr + TMEM_REC + h * QT, u);
+                tmem_ld16(tmem + lane_addr + TMEM_REC + h * QT + 16, u + 16);
                 float lsum = 0.0f;
 #pragma unroll
-                for (int k = 0; k < 64 / U_ROWS; ++k) {
-                    const int cnt = it * (64 / U_ROWS) + k, st = h * U_STAGES + cnt % U_STAGES;
-                    uint32_t v0[16];
-                    tmem_ld16(tmem + lane_addr + TMEM_REC + h * 64 + k * 16, v0);
+                for (int k = 0; k < QT / U_ROWS; ++k) {
+                    const int cnt = it * (QT / U_ROWS) + k, st = h * U_STAGES + cnt % U_STAGES;
                     mbar_wait(bar(U_FULL0 + st), (cnt / U_STAGES) & 1, 11, cnt);
                     const uint32_t us = sbase + U_OFF + st * U_STAGE + p * 4;
-                    tmem_ld_wait();
+                    if (k == 0) tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int t = t0 + k * 16 + j;
+                    for (int j = 0; j < U_ROWS; ++j) {
+                        const int t = t0 + k * U_ROWS + j;
                         float uv;
                         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(uv) : "r"(us + j * (BP * 4)));
-                        const float rr = (xin && t < a.m) ? __uint_as_float(v0[j]) - uv : 0.0f;
-                        u[k * 16 + j] = rr;
+                        const float rr = (xin && t < a.m) ? __uint_as_float(u[k * U_ROWS + j]) - uv : 0.0f;
+                        u[k * U_ROWS + j] = __float_as_uint(rr);
                         lsum = fmaf(rr, rr, lsum);
                     }
                     mbar_arrive(bar(U_EMPTY0 + st));
@@ -422,14 +428,15 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 c0 = clock64(); te[1] += c0 - c1;
                 if (it > 0) mbar_wait(bar(R_EMPTY), (it - 1) & 1, 12, it);
                 c1 = clock64(); te[2] += c1 - c0;
-                // ---- r -> three bf16 planes, own row p of box h (64 snapshots = 128 B = 8 chunks of 16 B) ----
-                const uint32_t rs = sbase + R_OFF + h * (BP * 128) + p * 128;
+                // ---- r -> three bf16 planes: row p of box (h >> 1), 16 B chunks (h & 1) * 4 .. +3 (8 snapshots each) ----
+                const uint32_t rs = sbase + R_OFF + (h >> 1) * (BP * 128) + p * 128;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
+                for (int c = 0; c < 4; ++c) {
                     uint32_t w1[4], w2[4], w3[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) split3_pair(u[c * 8 + 2 * e], u[c * 8 + 2 * e + 1], w1[e], w2[e], w3[e]);
-                    const uint32_t off = ((uint32_t)(c ^ (p & 7))) << 4;
+                    for (int ee = 0; ee < 4; ++ee)
+                        split3_pair(__uint_as_float(u[c * 8 + 2 * ee]), __uint_as_float(u[c * 8 + 2 * ee + 1]), w1[ee], w2[ee], w3[ee]);
+                    const uint32_t off = ((uint32_t)(((h & 1) * 4 + c) ^ (p & 7))) << 4;
                     st_shared_v4(rs + off, w1[0], w1[1], w1[2], w1[3]);
                     st_shared_v4(rs + R_PLANE + off, w2[0], w2[1], w2[2], w2[3]);
                     st_shared_v4(rs + 2 * R_PLANE + off, w3[0], w3[1], w3[2], w3[3]);
@@ -444,11 +451,11 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             a.dbg[blockIdx.x * 32 + 16] = clock64() - tstart;
         }
         // last tile's chain rule, then the E accumulators of this CTA
-        if (h == 1 && my_tiles > 0) chain_and_store(my_tiles - 1, blockIdx.x + (long long)(my_tiles - 1) * gridDim.x);
+        if (h == NQ - 1 && my_tiles > 0) chain_and_store(my_tiles - 1, blockIdx.x + (long long)(my_tiles - 1) * gridDim.x);
         if (total > 0) mbar_wait(bar(R_EMPTY), (total - 1) & 1, 13, total);
         tc_fence_after();
         float* Eo = a.Epart + (long long)blockIdx.x * a.kp_out * a.mld;
-        for (int slab = h; slab < nslab; slab += 2) {
+        for (int slab = h; slab < nslab; slab += NQ) {
             const int t = slab * BT + p;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
