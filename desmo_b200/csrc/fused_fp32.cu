@@ -319,6 +319,25 @@ void reduce_partials_launch(const float* Epart, int nx, long long ecount, const 
     reduce_partials_kernel<<<(unsigned)((ecount + 255) / 256), 256, 0, st>>>(Epart, nx, ecount, Spart, nslots, r, red);
 }
 
+// Chain rule for a D matrix left in ws.Dacc by the tensor-core kernel (same kernel the chunked FFMA path uses).
+int chain_rule_launch(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const float* P, const float* phi, const float* omega, float* dphi,
+                      const Workspace& ws, int slot_base, int* nslots, cudaStream_t st) {
+    (void)Kp;
+    FusedArgs a{};
+    a.P = P; a.phi = phi; a.omega = omega; a.dphi = dphi; a.Spart = ws.Spart; a.Dacc = ws.Dacc;
+    a.n = s->n; a.ld = s->ld; a.m = s->m; a.mld = s->mld; a.r = s->r; a.T = T; a.K = T + 3 * s->r;
+    a.scale = (float)(2.0 / ((double)s->n_global * (double)s->m));
+    a.mt = mt;
+    const long long ntiles = (a.ld + kTile - 1) / kTile;
+    const int gc = (int)(ntiles < 592 ? ntiles : 592);
+    const size_t sm = 8 * kScal * sizeof(double) + (size_t)(5 * kMaxR + a.K) * kTile * sizeof(float);
+    DESMO_CUDA(cudaFuncSetAttribute(chain_rule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    chain_rule_kernel<<<gc, kTile, sm, st>>>(a, slot_base);
+    DESMO_CUDA(cudaGetLastError());
+    *nslots = gc;
+    return DESMO_OK;
+}
+
 template <int KP>
 static int launch_fused(const FusedArgs& a, int sms, size_t smem_cap, cudaStream_t st, int* gx_out, int* nslots_out) {
     using L = FusedSmem<KP>;

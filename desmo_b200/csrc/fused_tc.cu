@@ -58,6 +58,7 @@ struct TcArgs {
     float* dphi;
     float* Epart;
     double* Spart;
+    float* Dacc;   // [Kp][ld] raw dG = R W^T rows (unscaled), consumed by the chain-rule kernel
     long long n, ld;
     int m, mld, r, T, K, nslab, kp_out;
     unsigned long long* dbg;  // optional per-CTA phase timers (cycles), 32 per CTA
@@ -144,6 +145,10 @@ __device__ __forceinline__ bool elect_one_sync() {
     asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %1;\n\t@px mov.s32 %0, 1;\n\t}\n" : "+r"(pred) : "r"(0xffffffffu));
     return pred != 0;
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // x = b1 + b2 + b3 (bf16 each, round-to-nearest): packs two consecutive elements (lo = first) per 32-bit word
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
     if (tid == 32) {
         mbar_init(bar(W_FULL0), 1); mbar_init(bar(W_FULL1), 1); mbar_init(bar(W_EMPTY0), 1); mbar_init(bar(W_EMPTY1), 1);
         mbar_init(bar(REC_FULL), 1); mbar_init(bar(REC_EMPTY), EPI_THREADS); mbar_init(bar(R_FULL), EPI_THREADS); mbar_init(bar(R_EMPTY), 1);
-        mbar_init(bar(G_FULL), EPI_THREADS); mbar_init(bar(G_EMPTY), 1); mbar_init(bar(D_FULL), 1); mbar_init(bar(D_EMPTY), 128);
+        mbar_init(bar(G_FULL), EPI_THREADS); mbar_init(bar(G_EMPTY), 1); mbar_init(bar(D_FULL), 1); mbar_init(bar(D_EMPTY), EPI_THREADS);
         for (int i = 0; i < NQ * U_STAGES; ++i) { mbar_init(bar(U_FULL0 + i), 1); mbar_init(bar(U_EMPTY0 + i), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -212,20 +217,33 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         }
     } else if (warp == 3 || warp == 2) {
         // ================= TMA producers: U chunks [8 snapshots][128 points]; each thread feeds the private rings of two quarters ==========
+        // A ring holds the first 24 of a quarter's 32 snapshots (3 stages = exactly one slab-tile), so the three boxes of the NEXT
+        // slab-tile are requested as soon as the current ones are consumed; the last 8 snapshots are fetched by the epilogue threads
+        // themselves one slab ahead (registers).  No divisions in the loop: one thread sustains ~1 TMA instruction per 400 cycles.
         if (elect_one_sync()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmU) : "memory");
+            const int h0 = (warp - 2) * 2;
+            int slab = 0;
+            uint32_t par = 1;
+            long long tile = blockIdx.x;
+            unsigned long long tp0 = 0;
+            const long long tps = clock64();
             for (int it = 0; it < total; ++it) {
-                const int slab = it % nslab;
-                const long long tile = blockIdx.x + (long long)(it / nslab) * gridDim.x;
-                for (int k = 0; k < QT / U_ROWS; ++k)
+#pragma unroll
+                for (int k = 0; k < U_STAGES; ++k)
+#pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
-                        const int h = (warp - 2) * 2 + hh;
-                        const int cnt = it * (QT / U_ROWS) + k, st = h * U_STAGES + cnt % U_STAGES;
-                        if (cnt >= U_STAGES) mbar_wait(bar(U_EMPTY0 + st), ((cnt / U_STAGES) - 1) & 1, 2, cnt);
+                        const int st = (h0 + hh) * U_STAGES + k;
+                        long long cp0 = clock64();
+                        if (it > 0) mbar_wait(bar(U_EMPTY0 + st), par, 2, it);
+                        tp0 += clock64() - cp0;
                         mbar_expect_tx(bar(U_FULL0 + st), U_STAGE);
-                        tma_load_2d(sbase + U_OFF + st * U_STAGE, &tmU, (int)(tile * BP), slab * BT + h * QT + k * U_ROWS, bar(U_FULL0 + st));
+                        tma_load_2d(sbase + U_OFF + st * U_STAGE, &tmU, (int)(tile * BP), slab * BT + (h0 + hh) * QT + k * U_ROWS, bar(U_FULL0 + st));
                     }
+                par ^= 1;
+                if (++slab == nslab) { slab = 0; tile += gridDim.x; }
             }
+            if (a.dbg) { a.dbg[blockIdx.x * 32 + 20 + (warp - 2) * 2] = tp0; a.dbg[blockIdx.x * 32 + 21 + (warp - 2) * 2] = clock64() - tps; }
         }
     } else if (warp == 1) {
         // ================================================ MMA issuer ================================================
@@ -320,38 +338,23 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         unsigned long long te[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const long long tstart = clock64();
 
-        auto chain_and_store = [&](int tile_local, long long tile) {
-            // D of the finished tile -> d mse/d phi, d omega, Phi^T Phi   (warps of quarter 3)
-            float dl[tc::KP], dph[kMaxR], dom[3 * kMaxR];
+        auto store_d = [&](int tile_local, long long tile) {
+            // D = R W^T of the finished tile: quarter h drains library columns 8h..8h+7 (three N-stacked blocks summed) to Dacc[j][x];
+            // the chain rule through POOL_DATA / sin / cos / tanh runs in a separate light kernel, off this kernel's critical path.
             const long long x = tile * BP + p;
             mbar_wait(bar(D_FULL), tile_local & 1, 8, tile_local);
             tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v0[16], v1[16], v2[16];
-                tmem_ld16(tmem + lane_addr + TMEM_D + c * 16, v0);
-                tmem_ld16(tmem + lane_addr + TMEM_D + KP + c * 16, v1);
-                tmem_ld16(tmem + lane_addr + TMEM_D + 2 * KP + c * 16, v2);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    dl[c * 16 + j] = ((__uint_as_float(v2[j]) + __uint_as_float(v1[j])) + __uint_as_float(v0[j])) * a.scale;
-            }
+            uint32_t v0[8], v1[8], v2[8];
+            tmem_ld8(tmem + lane_addr + TMEM_D + h * 8, v0);
+            tmem_ld8(tmem + lane_addr + TMEM_D + KP + h * 8, v1);
+            tmem_ld8(tmem + lane_addr + TMEM_D + 2 * KP + h * 8, v2);
+            tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(bar(D_EMPTY));
-            for (int i = 0; i < a.r; ++i) lat[i] = a.phi[(long long)i * a.ld + x] * a.P[(long long)i * a.ld + x];
-            chain_rule_point(a.mt, a.r, a.T, a.omega, lat, dl, dph, dom, 1);
-            for (int i = 0; i < a.r; ++i) a.dphi[(long long)i * a.ld + x] = dph[i] * a.P[(long long)i * a.ld + x];
-            const bool xin = x < a.n;
-            for (int i = 0; i < 3 * a.r; ++i) {
-                const float s = warp_sum(xin ? dom[i] : 0.0f);
-                if (lane == 0) red_s[q * kScal + 1 + kMaxR * kMaxR + i] += (double)s;
-            }
-            for (int i = 0; i < a.r; ++i)
-                for (int j = i; j < a.r; ++j) {
-                    const float s = warp_sum(lat[i] * lat[j]);
-                    if (lane == 0) red_s[q * kScal + 1 + i * kMaxR + j] += (double)s;
-                }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (h * 8 + j < a.kp_out)
+                    a.Dacc[(long long)(h * 8 + j) * a.ld + x] = (__uint_as_float(v2[j]) + __uint_as_float(v1[j])) + __uint_as_float(v0[j]);
         };
 
         int it = 0;
@@ -393,8 +396,15 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 mbar_arrive(bar(G_FULL));
                 te[6] += clock64() - cg0;
             }
-            if (h == NQ - 1 && tl > 0) chain_and_store(tl - 1, tile - gridDim.x);
+            if (tl > 0) store_d(tl - 1, tile - gridDim.x);
 
+            float ulast[U_ROWS];
+            auto load_last = [&](int slab2, long long x2, bool xin2) {  // snapshots 24..31 of this thread's quarter, straight from HBM/L2
+                const int tb = slab2 * BT + h * QT + 3 * U_ROWS;
+#pragma unroll
+                for (int j = 0; j < U_ROWS; ++j) ulast[j] = (xin2 && tb + j < a.m) ? __ldg(a.U + (long long)(tb + j) * a.ld + x2) : 0.0f;
+            };
+            load_last(0, x, xin);
             for (int slab = 0; slab < nslab; ++slab, ++it) {
                 const int t0 = slab * BT + h * QT;
                 long long c0 = clock64();
@@ -406,11 +416,13 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 tmem_ld16(tmem + lane_addr + TMEM_REC + h * QT + 16, u + 16);
                 float lsum = 0.0f;
 #pragma unroll
-                for (int k = 0; k < QT / U_ROWS; ++k) {
-                    const int cnt = it * (QT / U_ROWS) + k, st = h * U_STAGES + cnt % U_STAGES;
-                    mbar_wait(bar(U_FULL0 + st), (cnt / U_STAGES) & 1, 11, cnt);
+                for (int k = 0; k < U_STAGES; ++k) {
+                    const int st = h * U_STAGES + k;
+                    long long cu0 = clock64();
+                    mbar_wait(bar(U_FULL0 + st), it & 1, 11, it);
+                    te[4] += clock64() - cu0;
                     const uint32_t us = sbase + U_OFF + st * U_STAGE + p * 4;
-                    if (k == 0) tmem_ld_wait();
+                    if (k == 0) { long long ct0 = clock64(); tmem_ld_wait(); te[7] += clock64() - ct0; }
 #pragma unroll
                     for (int j = 0; j < U_ROWS; ++j) {
                         const int t = t0 + k * U_ROWS + j;
@@ -421,6 +433,13 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                         lsum = fmaf(rr, rr, lsum);
                     }
                     mbar_arrive(bar(U_EMPTY0 + st));
+                }
+#pragma unroll
+                for (int j = 0; j < U_ROWS; ++j) {  // last 8 snapshots of the quarter: prefetched into registers one slab ago
+                    const int t = t0 + 3 * U_ROWS + j;
+                    const float rr = (xin && t < a.m) ? __uint_as_float(u[3 * U_ROWS + j]) - ulast[j] : 0.0f;
+                    u[3 * U_ROWS + j] = __float_as_uint(rr);
+                    lsum = fmaf(rr, rr, lsum);
                 }
                 loss_acc += (double)lsum;
                 tc_fence_before();
@@ -443,6 +462,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 }
                 fence_async_smem();
                 mbar_arrive(bar(R_FULL));
+                if (slab + 1 < nslab) load_last(slab + 1, x, xin);  // flies while G3/G4 of this slab and G1 of the next run
                 te[3] += clock64() - c1;
             }
         }
@@ -450,8 +470,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             for (int i = 0; i < 8; ++i) a.dbg[blockIdx.x * 32 + 8 + i] = te[i];
             a.dbg[blockIdx.x * 32 + 16] = clock64() - tstart;
         }
+        if (a.dbg && lane == 0 && blockIdx.x == 0)
+            for (int i = 0; i < 8; ++i) a.dbg[8192 + e * 8 + i] = te[i];
         // last tile's chain rule, then the E accumulators of this CTA
-        if (h == NQ - 1 && my_tiles > 0) chain_and_store(my_tiles - 1, blockIdx.x + (long long)(my_tiles - 1) * gridDim.x);
+        if (my_tiles > 0) store_d(my_tiles - 1, blockIdx.x + (long long)(my_tiles - 1) * gridDim.x);
         if (total > 0) mbar_wait(bar(R_EMPTY), (total - 1) & 1, 13, total);
         tc_fence_after();
         float* Eo = a.Epart + (long long)blockIdx.x * a.kp_out * a.mld;
@@ -514,6 +536,8 @@ int fused_tc_supported(const desmo_shape* s, int Kp) {
 }
 
 void reduce_partials_launch(const float* Epart, int nx, long long ecount, const double* Spart, int nslots, int r, float* red, cudaStream_t st);
+int chain_rule_launch(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const float* P, const float* phi, const float* omega, float* dphi,
+                      const Workspace& ws, int slot_base, int* nslots, cudaStream_t st);
 
 int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const float* U, const float* P, const float* phi,
              const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st) {
@@ -543,7 +567,7 @@ int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const flo
         if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(U) failed (%d)", (int)cr); return DESMO_ERR_CUDA; }
     }
     TcArgs a{};
-    a.U = U; a.P = P; a.phi = phi; a.omega = omega; a.dphi = dphi; a.Epart = ws.Epart; a.Spart = ws.Spart;
+    a.U = U; a.P = P; a.phi = phi; a.omega = omega; a.dphi = dphi; a.Epart = ws.Epart; a.Spart = ws.Spart; a.Dacc = ws.Dacc;
     a.n = s->n; a.ld = s->ld; a.m = s->m; a.mld = s->mld; a.r = s->r; a.T = T; a.K = T + 3 * s->r;
     a.nslab = (s->m + tc::BT - 1) / tc::BT;
     a.dbg = nullptr;
@@ -565,7 +589,10 @@ int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const flo
     DESMO_CUDA(cudaFuncSetAttribute(fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
     fused_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, tm, tmu);
     DESMO_CUDA(cudaGetLastError());
-    reduce_partials_launch(ws.Epart, grid, (long long)Kp * s->mld, ws.Spart, grid, s->r, red, st);
+    int nchain = 0;
+    int rc = chain_rule_launch(s, mt, T, Kp, P, phi, omega, dphi, ws, grid, &nchain, st);
+    if (rc) return rc;
+    reduce_partials_launch(ws.Epart, grid, (long long)Kp * s->mld, ws.Spart, grid + nchain, s->r, red, st);
     DESMO_CUDA(cudaGetLastError());
     return DESMO_OK;
 }

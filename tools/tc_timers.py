@@ -16,12 +16,18 @@ torch.cuda.synchronize()
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ev0.record(); e.fused_residual_grad(); ev1.record(); torch.cuda.synchronize()
 print("kernel+reduce ms", ev0.elapsed_time(ev1), "tiles/CTA", n / 128 / 148)
-out = np.zeros(148 * 32, np.uint64)
+out = np.zeros(16384, np.uint64)
 _lib.check(e.lib.desmo_debug_timers(ctypes.byref(e.shape), e.workspace.data_ptr(), out.ctypes.data_as(ctypes.c_void_p), out.size))
-t = out.reshape(148, 32).astype(np.float64)
+t = out[:148 * 32].reshape(148, 32).astype(np.float64)
 nst = n / 128 / 148 * 8
 names = ["mma:wait W_FULL", "mma:wait REC_EMPTY", "mma:wait G_FULL", "mma:wait R_FULL", "mma:wait D_EMPTY", "", "", "",
-         "epi:wait REC_FULL", "epi:phase A", "epi:wait R_EMPTY", "epi:phase B", "", "epi:wait G_EMPTY", "epi:G compute+store", "", "epi:total"]
+         "epi:wait REC_FULL", "epi:phase A", "epi:wait R_EMPTY", "epi:phase B", "epi:  in A: wait U_FULL", "epi:wait G_EMPTY", "epi:G compute+store", "epi:  in A: tmem ld wait", "epi:total",
+         "", "", "", "prod0:wait U_EMPTY", "prod0:total", "prod1:wait U_EMPTY", "prod1:total"]
 for i, nm in enumerate(names):
     if nm:
         print(f"{nm:22s} mean {t[:, i].mean() / nst:9.0f} cycles/slab-tile   (min {t[:, i].min() / nst:8.0f}, max {t[:, i].max() / nst:8.0f})")
+
+w = out[8192:8192 + 128].reshape(16, 8).astype(np.float64) / nst
+print("per-warp (CTA 0)  e: q h | wait REC_FULL | phase A (of which U_FULL) | wait R_EMPTY | phase B | G")
+for e_ in range(16):
+    print(f"  warp {e_:2d}: q{e_ & 3} h{e_ >> 2} | {w[e_,0]:7.0f} | {w[e_,1]:7.0f} ({w[e_,4]:5.0f}) | {w[e_,2]:6.0f} | {w[e_,3]:6.0f} | {w[e_,6]:5.0f}")
