@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 fp32 FFMA, 2 tcgen05")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-pod", action="store_true", help="profiling runs: random orthonormal-scale modes instead of the POD init")
     ap.add_argument("--cpu-sample", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -189,7 +190,12 @@ def main():
         model = DESMO(n, m, p, r, 10000, device=dev, n_global=n_global, path=args.path)
     e = model.engine
     e.U = synth_on_device(torch, n, m, dev, seed=2, x_offset=rank * n, n_global=n_global)
-    sigma = e.pod_from_snapshot()  # POD init on the device (method of snapshots)
+    if args.no_pod:
+        gen = torch.Generator(device=dev).manual_seed(5)
+        e.P[:, :n] = torch.randn(r, n, device=dev, generator=gen) / n ** 0.5
+        sigma = torch.zeros(r)
+    else:
+        sigma = e.pod_from_snapshot()  # POD init on the device (method of snapshots)
     torch.cuda.synchronize()
     trainer = DesmoTrainer(model, sched_every=10 ** 9, use_cuda_graph=True)  # no host sync inside the timed region
 
@@ -291,9 +297,17 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "kernel": "fused_residual_grad", "kernel_ms": kms, "peak_source": peak_src,
                              "algorithmic_bytes": alg_bytes},
-                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": 4 * args.steps,
+                "clocks": clk.summary(), "e2e": e2e,
+                "gpu_launches": (5 if e.uses_tensor_cores() else 4) * args.steps + (1 if world > 1 else 0) * args.steps,
                 "losses_last_step": losses, "pod_sigma": [float(v) for v in sigma.tolist()],
-                "path": "tcgen05" if False else ("auto" if args.path == 0 else ("fp32" if args.path == 1 else "tcgen05"))}
+                "path": "tcgen05 (bf16x3 split)" if e.uses_tensor_cores() else "fp32 ffma"}
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as fh:
+                tr = json.load(fh)
+            if tr.get("points_per_gpu") == n and tr.get("path") == line["path"]:
+                line["roofline"]["traffic"] = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
         if not args.no_cpu and world == 1:
             try:
                 line["cpu_baseline"] = cpu_reference_leg(n, m, r, p, nF, 5, 1, args.cpu_sample or None)

@@ -101,6 +101,10 @@ class DesmoEngine:
         self.step_dev.zero_()
 
     # ------------------------------------------------------------------ launches
+    def uses_tensor_cores(self) -> bool:
+        """True when desmo_fused_residual_grad dispatches to the tcgen05 kernel for this shape / path."""
+        return self.shape.path != _lib.PATH_FP32 and self.Kp <= 32 and self.mld <= 1024
+
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 

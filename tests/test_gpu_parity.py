@@ -285,3 +285,22 @@ def test_headline_size_properties():
     E1 = e.red[:e.Kp * e.mld].clone()
     assert rel(E2.cpu().numpy(), 2.0 * E1.cpu().numpy()) < 1e-6
     assert E0.abs().max() > 0
+
+
+def test_registered_torch_custom_ops_match_engine():
+    """The same step through torch.ops.desmo_b200.* (custom-op registration of the C ABI)."""
+    import desmo_b200.ops as ops
+
+    _, modes, snap, prm = make_case("aneurysm", 1000, 100, 4, 2, omega_init=10.0)
+    a, b = _engine(prm, modes, snap, 0), _engine(prm, modes, snap, 0)
+    for e in (a, b):
+        e.set_hyper((1e-2, 1e-3, 1e-2, 1e-2), 1e-3, 1e-4)
+    for _ in range(3):
+        a.train_step()
+        ops.engine_step_via_ops(b)
+    torch.cuda.synchronize()
+    for k, v in engine_params(a).items():
+        assert np.array_equal(v, engine_params(b)[k]), k
+    with pytest.raises(Exception):
+        torch.ops.desmo_b200.fused_residual_grad(a.U.cpu(), a.P.cpu(), a.phi.cpu(), a.omega.cpu(), a.W.cpu(), a.dphi.cpu(), a.red.cpu(),
+                                                 a.workspace.cpu(), a.n, a.n, a.m, a.r, a.polyorder, 0, 0)
