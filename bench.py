@@ -22,6 +22,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("DESMO_KERNEL_EVENTS", "1")  # lets the library time its dominant kernel with CUDA events
 
 WORKLOADS = {
     # name: (points per GPU, m, r, polyorder, nF)
@@ -232,7 +233,9 @@ def main():
         e.build_w(False)
         torch.cuda.synchronize()
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kms = 0.0
+        kms = 0.0      # the fused call (dominant kernel + chain rule + partial reduction), torch events on the current stream
+        kms_dom = 0.0  # the dominant kernel alone, CUDA events recorded inside the library on the launching stream
+        dom = ctypes.c_float(0.0)
         for _ in range(args.steps):
             if l2_flush is not None:
                 l2_flush.fill_(1)
@@ -241,7 +244,10 @@ def main():
             k1.record()
             torch.cuda.synchronize()
             kms += k0.elapsed_time(k1)
+            _lib.check(e.lib.desmo_last_fused_kernel_ms(ctypes.byref(dom)), "desmo_last_fused_kernel_ms")
+            kms_dom += dom.value
         kms /= args.steps
+        kms_dom /= args.steps
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -288,14 +294,15 @@ def main():
     if rank == 0:
         peak, peak_src = load_peaks()
         alg_bytes = 4.0 * n * m + 12.0 * n * r + 8.0 * e.K * m  # U once; phi, P in, dphi out; W in, E out
-        achieved = alg_bytes / (kms * 1e-3) / 1e9
+        achieved = alg_bytes / (kms_dom * 1e-3) / 1e9
         line = {"metric": METRIC, "value": world / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": cfg,
                 "global_iters_per_s": 1.0 / (ms_step * 1e-3),
                 "snapshot_gbs": world * 4.0 * n * m / (ms_step * 1e-3) / 1e9,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "fused_residual_grad", "kernel_ms": kms, "peak_source": peak_src,
+                             "traffic": None, "kernel": "fused_tc_kernel" if e.uses_tensor_cores() else "fused_fp32_kernel", "kernel_ms": kms_dom,
+                             "fused_call_ms": kms, "peak_source": peak_src,
                              "algorithmic_bytes": alg_bytes},
                 "clocks": clk.summary(), "e2e": e2e,
                 "gpu_launches": (5 if e.uses_tensor_cores() else 4) * args.steps + (1 if world > 1 else 0) * args.steps,
@@ -313,9 +320,15 @@ def main():
                 line["cpu_baseline"] = cpu_reference_leg(n, m, r, p, nF, 5, 1, args.cpu_sample or None)
             except Exception as ex:
                 line["cpu_baseline"] = {"value": None, "error": str(ex)[:200]}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # tear-down of a process group whose collectives were captured in a CUDA graph can block; everything is measured and
+        # printed, so leave without the destructor dance (exit code 0 for torchrun)
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

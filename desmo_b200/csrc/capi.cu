@@ -259,6 +259,13 @@ int desmo_library_colnorm2(const desmo_shape* s, const float* P, const float* ph
     return launch_colnorm2(a, (cudaStream_t)stream);
 }
 
+int desmo_last_fused_kernel_ms(float* ms) {
+    if (!ms) { set_error("desmo_last_fused_kernel_ms: null"); return DESMO_ERR_ARG; }
+    const int rc = fused_event_ms(ms);
+    if (rc) set_error("desmo_last_fused_kernel_ms: no timed launch (set DESMO_KERNEL_EVENTS=1 before the first call)");
+    return rc;
+}
+
 int desmo_debug_timers(const desmo_shape* s, void* workspace, uint64_t* out_host, int32_t count) {
     (void)s; (void)workspace;
     if (!out_host || count < 1) { set_error("desmo_debug_timers: bad argument"); return DESMO_ERR_ARG; }

@@ -75,6 +75,8 @@ int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const flo
              const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st);
 int fused_tc_supported(const desmo_shape* s, int Kp);
 int tc_debug_read(uint64_t* out, int count);
+int fused_event_ms(float* ms);
+void fused_event_record(int which, cudaStream_t st);
 int launch_update(const UpdateArgs& a, cudaStream_t st);
 int launch_reconstruct(const EvalArgs& a, cudaStream_t st);
 int launch_colnorm2(const EvalArgs& a, cudaStream_t st);

@@ -360,7 +360,9 @@ static int launch_fused(const FusedArgs& a, int sms, size_t smem_cap, cudaStream
     const int gx = (int)(ntiles < per_chunk ? ntiles : per_chunk);
     DESMO_CUDA(cudaFuncSetAttribute(fused_fp32_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes(mc)));
     if (nchunk > 1) DESMO_CUDA(cudaMemsetAsync(b.Dacc, 0, sizeof(float) * (size_t)KP * a.ld, st));
+    fused_event_record(0, st);
     fused_fp32_kernel<KP><<<dim3(gx, nchunk), kTile, L::bytes(mc), st>>>(b);
+    fused_event_record(1, st);
     DESMO_CUDA(cudaGetLastError());
     int nslots = gx * nchunk;
     if (nchunk > 1) {

@@ -75,26 +75,24 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ unsigned long long* g_tc_dbg = nullptr;  // host-mapped diagnostics buffer (DESMO_TC_DEBUG), survives a trap
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0, int iter = 0) {
+template <bool kDebug>
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int tag, int iter) {
     uint32_t done = 0;
     unsigned spins = 0;
     while (!done) {
-        asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (!done && g_tc_dbg && ++spins >= (1u << 22)) {  // only armed in debug runs: report who is stuck, later abort the grid
-            if (spins == (1u << 22)) {
-                unsigned long long* d = g_tc_dbg + 4096 + (blockIdx.x * 12 + (threadIdx.x >> 5)) * 4;
-                d[0] = 0xdead0000ull | (unsigned)tag; d[1] = (unsigned long long)iter; d[2] = parity; d[3] = threadIdx.x;
-                __threadfence_system();
+        // the suspend-time hint lets the hardware park the thread instead of burning issue slots the epilogue math needs
+        asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(kDebug ? 2000u : 0x989680u) : "memory");
+        if (kDebug) {
+            if (!done && ++spins >= (1u << 20)) {  // debug runs only: report who is stuck, later abort the grid
+                if (spins == (1u << 20) && g_tc_dbg) {
+                    unsigned long long* d = g_tc_dbg + 4096 + (blockIdx.x * 20 + (threadIdx.x >> 5)) * 4;
+                    d[0] = 0xdead0000ull | (unsigned)tag; d[1] = (unsigned long long)iter; d[2] = parity; d[3] = threadIdx.x;
+                    __threadfence_system();
+                }
+                if (spins > (1u << 22)) __trap();
             }
-            if (spins > (1u << 24)) __trap();
         }
-    }
-}
-__device__ __forceinline__ void dbg_mark(int it, int step) {  // debug runs only: last point reached by each warp
-    if (g_tc_dbg && (threadIdx.x & 31) == 0) {
-        volatile unsigned long long* d = g_tc_dbg + 12288 + blockIdx.x * 12 + (threadIdx.x >> 5);
-        *d = ((unsigned long long)it << 8) | (unsigned)step;
     }
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -167,6 +165,7 @@ __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t& w1, ui
 __device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
 
+template <bool kDebug>
 __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmW,
                                                                           const __grid_constant__ CUtensorMap tmU) {
     using namespace tc;
@@ -180,6 +179,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
     enum { W_FULL0 = 0, W_FULL1, W_EMPTY0, W_EMPTY1, REC_FULL, REC_EMPTY, R_FULL, R_EMPTY, G_FULL, G_EMPTY, D_FULL, D_EMPTY,
            U_FULL0, U_EMPTY0 = U_FULL0 + NQ * U_STAGES };
     auto bar = [&](int i) { return smem_u32(&bars[i]); };
+    auto mbar_wait = [&](uint32_t b, uint32_t parity, int tag = 0, int iter = 0) { mbar_wait_t<kDebug>(b, parity, tag, iter); };
+    auto now = [&]() -> long long { return kDebug ? clock64() : 0ll; };
 
     const int nslab = a.nslab;
     const long long ntiles = a.ld / BP;
@@ -227,23 +228,23 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             uint32_t par = 1;
             long long tile = blockIdx.x;
             unsigned long long tp0 = 0;
-            const long long tps = clock64();
+            const long long tps = now();
             for (int it = 0; it < total; ++it) {
 #pragma unroll
                 for (int k = 0; k < U_STAGES; ++k)
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
                         const int st = (h0 + hh) * U_STAGES + k;
-                        long long cp0 = clock64();
+                        long long cp0 = now();
                         if (it > 0) mbar_wait(bar(U_EMPTY0 + st), par, 2, it);
-                        tp0 += clock64() - cp0;
+                        tp0 += now() - cp0;
                         mbar_expect_tx(bar(U_FULL0 + st), U_STAGE);
                         tma_load_2d(sbase + U_OFF + st * U_STAGE, &tmU, (int)(tile * BP), slab * BT + (h0 + hh) * QT + k * U_ROWS, bar(U_FULL0 + st));
                     }
                 par ^= 1;
                 if (++slab == nslab) { slab = 0; tile += gridDim.x; }
             }
-            if (a.dbg) { a.dbg[blockIdx.x * 32 + 20 + (warp - 2) * 2] = tp0; a.dbg[blockIdx.x * 32 + 21 + (warp - 2) * 2] = clock64() - tps; }
+            if (a.dbg) { a.dbg[blockIdx.x * 32 + 20 + (warp - 2) * 2] = tp0; a.dbg[blockIdx.x * 32 + 21 + (warp - 2) * 2] = now() - tps; }
         }
     } else if (warp == 1) {
         // ================================================ MMA issuer ================================================
@@ -253,13 +254,13 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             unsigned long long tm[6] = {0, 0, 0, 0, 0, 0};
             auto issue_g1 = [&](int it) {
                 const int buf = it & 1, slab = it % nslab, tl = it / nslab;
-                long long c0 = clock64();
+                long long c0 = now();
                 mbar_wait(bar(W_FULL0 + buf), (it >> 1) & 1, 3, it);
-                long long c1 = clock64(); tm[0] += c1 - c0;
+                long long c1 = now(); tm[0] += c1 - c0;
                 if (it > 0) mbar_wait(bar(REC_EMPTY), (it - 1) & 1, 4, it);
-                c0 = clock64(); tm[1] += c0 - c1;
+                c0 = now(); tm[1] += c0 - c1;
                 if (slab == 0) mbar_wait(bar(G_FULL), tl & 1, 5, it);
-                c1 = clock64(); tm[2] += c1 - c0;
+                c1 = now(); tm[2] += c1 - c0;
                 tc_fence_after();
                 // A = G_s MN-major (M = points, 2 boxes LBO = 4096), B = W_s MN-major (N = snapshots, 2 boxes LBO = W_BOX)
                 const uint32_t ga_lo = ((sbase + G_OFF) >> 4) | ((KP * 128u >> 4) << 16);
@@ -277,11 +278,11 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             };
             auto issue_g34 = [&](int it) {
                 const int buf = it & 1, slab = it % nslab, tl = it / nslab;
-                long long c0 = clock64();
+                long long c0 = now();
                 mbar_wait(bar(R_FULL), it & 1, 6, it);
-                long long c1 = clock64(); tm[3] += c1 - c0;
+                long long c1 = now(); tm[3] += c1 - c0;
                 if (slab == 0 && tl > 0) mbar_wait(bar(D_EMPTY), (tl - 1) & 1, 7, it);
-                c0 = clock64(); tm[4] += c0 - c1;
+                c0 = now(); tm[4] += c0 - c1;
                 tc_fence_after();
                 const uint32_t rk_lo = ((sbase + R_OFF) >> 4) | (1u << 16);                       // R_s K-major (G3 A)
                 const uint32_t rm_lo = ((sbase + R_OFF) >> 4) | ((BP * 128u >> 4) << 16);         // R_s MN-major (G4 A), LBO = 16384
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         double loss_acc = 0.0;
         float lat[kMaxR];
         unsigned long long te[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const long long tstart = clock64();
+        const long long tstart = now();
 
         auto store_d = [&](int tile_local, long long tile) {
             // D = R W^T of the finished tile: quarter h drains library columns 8h..8h+7 (three N-stacked blocks summed) to Dacc[j][x];
@@ -362,15 +363,15 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             const long long tile = blockIdx.x + (long long)tl * gridDim.x;
             const long long x = tile * BP + p;
             const bool xin = x < a.n;
-            long long cg0 = clock64();
+            long long cg0 = now();
             {
                 // ---- library row of this point (CYL:538-548,565-567), split into bf16 planes, G_s[lib rows][p contiguous].
                 //      The four quarters share the work (quarter h takes library terms j = h, h+4, ...).  Rolled loops on purpose:
                 //      this runs once per tile, and straight-line code here only thrashes the I-cache. ----
                 for (int i = 0; i < a.r; ++i) lat[i] = a.phi[(long long)i * a.ld + x] * a.P[(long long)i * a.ld + x];
-                long long cg1 = clock64();
+                long long cg1 = now();
                 if (tl > 0) mbar_wait(bar(G_EMPTY), (tl - 1) & 1, 9, tl);
-                cg0 = clock64(); te[5] += cg0 - cg1;
+                cg0 = now(); te[5] += cg0 - cg1;
                 const uint32_t gs = sbase + G_OFF + (p >> 6) * (KP * 128);
                 const uint32_t pb = (p & 63) * 2;
 #pragma unroll 1
@@ -394,41 +395,46 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 }
                 fence_async_smem();
                 mbar_arrive(bar(G_FULL));
-                te[6] += clock64() - cg0;
+                te[6] += now() - cg0;
             }
             if (tl > 0) store_d(tl - 1, tile - gridDim.x);
 
+            float lsum = 0.0f;  // fp32 over the 256 residuals of a tile, folded into the fp64 accumulator once per tile (FP64 adds are slow)
             float ulast[U_ROWS];
-            auto load_last = [&](int slab2, long long x2, bool xin2) {  // snapshots 24..31 of this thread's quarter, straight from HBM/L2
+            auto load_last = [&](int slab2) {  // snapshots 24..31 of this thread's quarter, straight from HBM/L2
                 const int tb = slab2 * BT + h * QT + 3 * U_ROWS;
+                const float* up = a.U + (long long)tb * a.ld + x;
+                if (xin && tb + U_ROWS <= a.m) {
 #pragma unroll
-                for (int j = 0; j < U_ROWS; ++j) ulast[j] = (xin2 && tb + j < a.m) ? __ldg(a.U + (long long)(tb + j) * a.ld + x2) : 0.0f;
+                    for (int j = 0; j < U_ROWS; ++j, up += a.ld) ulast[j] = __ldg(up);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < U_ROWS; ++j, up += a.ld) ulast[j] = (xin && tb + j < a.m) ? __ldg(up) : 0.0f;
+                }
             };
-            load_last(0, x, xin);
+            load_last(0);
             for (int slab = 0; slab < nslab; ++slab, ++it) {
                 const int t0 = slab * BT + h * QT;
-                long long c0 = clock64();
+                long long c0 = now();
                 mbar_wait(bar(REC_FULL), it & 1, 10, it);
-                long long c1 = clock64(); te[0] += c1 - c0;
+                long long c1 = now(); te[0] += c1 - c0;
                 tc_fence_after();
                 uint32_t u[QT];  // Rec of this thread's 32 snapshots, then r = Rec - U in place
                 tmem_ld16(tmem + lane_addr + TMEM_REC + h * QT, u);
                 tmem_ld16(tmem + lane_addr + TMEM_REC + h * QT + 16, u + 16);
-                float lsum = 0.0f;
+                const bool interior = xin && (t0 + QT <= a.m);  // no masking needed (all but the ragged last tile / slab)
 #pragma unroll
                 for (int k = 0; k < U_STAGES; ++k) {
                     const int st = h * U_STAGES + k;
-                    long long cu0 = clock64();
                     mbar_wait(bar(U_FULL0 + st), it & 1, 11, it);
-                    te[4] += clock64() - cu0;
                     const uint32_t us = sbase + U_OFF + st * U_STAGE + p * 4;
-                    if (k == 0) { long long ct0 = clock64(); tmem_ld_wait(); te[7] += clock64() - ct0; }
+                    if (k == 0) tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < U_ROWS; ++j) {
-                        const int t = t0 + k * U_ROWS + j;
                         float uv;
                         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(uv) : "r"(us + j * (BP * 4)));
-                        const float rr = (xin && t < a.m) ? __uint_as_float(u[k * U_ROWS + j]) - uv : 0.0f;
+                        float rr = __uint_as_float(u[k * U_ROWS + j]) - uv;
+                        if (!interior) rr = (xin && t0 + k * U_ROWS + j < a.m) ? rr : 0.0f;
                         u[k * U_ROWS + j] = __float_as_uint(rr);
                         lsum = fmaf(rr, rr, lsum);
                     }
@@ -436,17 +442,17 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 }
 #pragma unroll
                 for (int j = 0; j < U_ROWS; ++j) {  // last 8 snapshots of the quarter: prefetched into registers one slab ago
-                    const int t = t0 + 3 * U_ROWS + j;
-                    const float rr = (xin && t < a.m) ? __uint_as_float(u[3 * U_ROWS + j]) - ulast[j] : 0.0f;
+                    float rr = __uint_as_float(u[3 * U_ROWS + j]) - ulast[j];
+                    if (!interior) rr = (xin && t0 + 3 * U_ROWS + j < a.m) ? rr : 0.0f;
                     u[3 * U_ROWS + j] = __float_as_uint(rr);
                     lsum = fmaf(rr, rr, lsum);
                 }
-                loss_acc += (double)lsum;
                 tc_fence_before();
                 mbar_arrive(bar(REC_EMPTY));
-                c0 = clock64(); te[1] += c0 - c1;
+                if (slab + 1 < nslab) load_last(slab + 1);  // a whole phase B + G3/G4 ahead of its use
+                c0 = now(); te[1] += c0 - c1;
                 if (it > 0) mbar_wait(bar(R_EMPTY), (it - 1) & 1, 12, it);
-                c1 = clock64(); te[2] += c1 - c0;
+                c1 = now(); te[2] += c1 - c0;
                 // ---- r -> three bf16 planes: row p of box (h >> 1), 16 B chunks (h & 1) * 4 .. +3 (8 snapshots each) ----
                 const uint32_t rs = sbase + R_OFF + (h >> 1) * (BP * 128) + p * 128;
 #pragma unroll
@@ -462,13 +468,13 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 }
                 fence_async_smem();
                 mbar_arrive(bar(R_FULL));
-                if (slab + 1 < nslab) load_last(slab + 1, x, xin);  // flies while G3/G4 of this slab and G1 of the next run
-                te[3] += clock64() - c1;
+                te[3] += now() - c1;
             }
+            loss_acc += (double)lsum;
         }
         if (a.dbg && tid == 128) {
             for (int i = 0; i < 8; ++i) a.dbg[blockIdx.x * 32 + 8 + i] = te[i];
-            a.dbg[blockIdx.x * 32 + 16] = clock64() - tstart;
+            a.dbg[blockIdx.x * 32 + 16] = now() - tstart;
         }
         if (a.dbg && lane == 0 && blockIdx.x == 0)
             for (int i = 0; i < 8; ++i) a.dbg[8192 + e * 8 + i] = te[i];
@@ -508,6 +514,23 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
 }
 
 // ------------------------------------------------------------------------------------------------- host side
+static cudaEvent_t g_ev[2] = {nullptr, nullptr};
+static bool g_ev_valid = false;
+int fused_event_ms(float* ms) {  // duration of the last dominant-kernel launch (DESMO_KERNEL_EVENTS=1); synchronises
+    if (!g_ev_valid) return DESMO_ERR_ARG;
+    if (cudaEventSynchronize(g_ev[1]) != cudaSuccess) return DESMO_ERR_CUDA;
+    return cudaEventElapsedTime(ms, g_ev[0], g_ev[1]) == cudaSuccess ? DESMO_OK : DESMO_ERR_CUDA;
+}
+void fused_event_record(int which, cudaStream_t st) {
+    static const bool on = getenv("DESMO_KERNEL_EVENTS") != nullptr;
+    if (!on) return;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return;  // never inside a graph capture
+    if (!g_ev[0]) { cudaEventCreate(&g_ev[0]); cudaEventCreate(&g_ev[1]); }
+    cudaEventRecord(g_ev[which], st);
+    if (which == 1) g_ev_valid = true;
+}
+
 static unsigned long long* g_dbg_host = nullptr;
 constexpr size_t kDbgWords = 16384;
 int tc_debug_read(uint64_t* out, int count) {
@@ -586,8 +609,15 @@ int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const flo
     a.mt = mt;
     const long long ntiles = s->ld / tc::BP;
     const int grid = (int)(ntiles < sms ? ntiles : sms);
-    DESMO_CUDA(cudaFuncSetAttribute(fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-    fused_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, tm, tmu);
+    fused_event_record(0, st);
+    if (a.dbg) {
+        DESMO_CUDA(cudaFuncSetAttribute(fused_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+        fused_tc_kernel<true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, tm, tmu);
+    } else {
+        DESMO_CUDA(cudaFuncSetAttribute(fused_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+        fused_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, tm, tmu);
+    }
+    fused_event_record(1, st);
     DESMO_CUDA(cudaGetLastError());
     int nchain = 0;
     int rc = chain_rule_launch(s, mt, T, Kp, P, phi, omega, dphi, ws, grid, &nchain, st);

@@ -118,6 +118,10 @@ int desmo_reconstruct(const desmo_shape* s, const float* P, const float* phi, co
 int desmo_library_colnorm2(const desmo_shape* s, const float* P, const float* phi, const float* omega, float* out_k,
                            void* stream);
 
+/* Measurement: device time (CUDA events on the launching stream) of the dominant kernel of the last
+ * desmo_fused_residual_grad call, recorded when DESMO_KERNEL_EVENTS is set in the environment.  Synchronous. */
+int desmo_last_fused_kernel_ms(float* ms);
+
 /* Diagnostics: per-CTA phase timers (cycles) of the tcgen05 fused kernel, recorded when DESMO_TC_DEBUG is set in the
  * environment; 16 counters per CTA.  Synchronous. */
 int desmo_debug_timers(const desmo_shape* s, void* workspace, uint64_t* out_host, int32_t count);
