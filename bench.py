@@ -195,8 +195,18 @@ def main():
         gen = torch.Generator(device=dev).manual_seed(5)
         e.P[:, :n] = torch.randn(r, n, device=dev, generator=gen) / n ** 0.5
         sigma = torch.zeros(r)
+        pod_info = None
     else:
         sigma = e.pod_from_snapshot()  # POD init on the device (method of snapshots)
+        pod_info = dict(e.pod_timing)
+        # Gram = 2 n m^2 useful flop; on the tensor pipe it is executed as 6 bf16 passes over 128-padded tiles (upper triangle)
+        nt = (m + 127) // 128
+        pod_info["gram_tflops_fp32_equiv"] = 2.0 * n * m * m / (pod_info["gram_ms"] * 1e-3) / 1e12
+        pod_info["gram_tensor_tflops_bf16"] = 6 * 2.0 * n * (nt * (nt + 1) // 2) * 128 * 128 / (pod_info["gram_ms"] * 1e-3) / 1e12
+        try:
+            pod_info["gram_tensor_pipe_util"] = pod_info["gram_tensor_tflops_bf16"] / float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        except Exception:
+            pass
     torch.cuda.synchronize()
     trainer = DesmoTrainer(model, sched_every=10 ** 9, use_cuda_graph=True)  # no host sync inside the timed region
 
@@ -306,7 +316,7 @@ def main():
                              "algorithmic_bytes": alg_bytes},
                 "clocks": clk.summary(), "e2e": e2e,
                 "gpu_launches": (5 if e.uses_tensor_cores() else 4) * args.steps + (1 if world > 1 else 0) * args.steps,
-                "losses_last_step": losses, "pod_sigma": [float(v) for v in sigma.tolist()],
+                "losses_last_step": losses, "pod_sigma": [float(v) for v in sigma.tolist()], "pod_init": pod_info,
                 "path": "tcgen05 (bf16x3 split)" if e.uses_tensor_cores() else "fp32 ffma"}
         try:
             with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as fh:

@@ -98,6 +98,7 @@ int carve_workspace(const desmo_shape* s, const Dims& d, void* base, Workspace* 
     ws->Epart = reinterpret_cast<float*>(b + off);  off = align_up(off + sizeof(float) * (size_t)sms * d.Kp * s->mld, 256);
     ws->l1 = reinterpret_cast<float*>(b + off);     off = align_up(off + 256, 256);
     ws->tc = reinterpret_cast<float*>(b + off);     off = align_up(off + sizeof(float) * 2 * (size_t)(d.Kp > 32 ? d.Kp : 32) * s->mld, 256);  // >= 3 bf16 planes [32][mld]
+    ws->gram = reinterpret_cast<float*>(b + off);   off = align_up(off + sizeof(float) * (size_t)sms * 128 * 128, 256);
     ws->Dacc = reinterpret_cast<float*>(b + off);   off = align_up(off + sizeof(float) * (size_t)d.Kp * s->ld, 256);
     ws->bytes = off;
     return DESMO_OK;
@@ -280,7 +281,9 @@ int desmo_pod_gram(const desmo_shape* s, const float* U, float* C, void* workspa
     if ((rc = device_ok())) return rc;
     if (!U || !C) { set_error("desmo_pod_gram: null pointer"); return DESMO_ERR_ARG; }
     if (s->path != DESMO_PATH_FP32 && workspace) {
-        rc = pod_gram_tc(s, U, C, workspace, (cudaStream_t)stream);
+        Workspace ws;
+        if ((rc = carve_workspace(s, d, workspace, &ws))) return rc;
+        rc = pod_gram_tc(s, U, C, ws.gram, (cudaStream_t)stream);
         if (rc != DESMO_ERR_UNSUPPORTED) return rc;  // shapes the tensor-core Gram does not cover run on the FFMA Gram kernel
     }
     return pod_gram_fp32(s, U, C, (cudaStream_t)stream);

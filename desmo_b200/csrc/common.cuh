@@ -29,7 +29,8 @@ struct Workspace {  // device-side carve-up of the caller's workspace; computed 
     double* Spart;   // [kMaxSlots][kScal]
     float* Dacc;     // [Kp][ld]   (only when the time axis is chunked)
     float* l1;       // [1] sum |gates| before the update
-    float* tc;       // tcgen05 path scratch (W hi/lo etc.)
+    float* tc;       // tcgen05 path scratch (bf16 planes of W)
+    float* gram;     // [SMs][128*128] per-CTA partial Gram tiles (tcgen05 Gram)
     size_t bytes;
 };
 

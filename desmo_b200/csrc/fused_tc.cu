@@ -25,6 +25,7 @@ constexpr int KP = 32;          // padded library size handled by this kernel
 constexpr int BP = 128;         // points per tile  (MMA M of G1/G3, K of G4)
 constexpr int BT = 128;         // snapshots per slab (MMA N of G1, K of G3, M of G4)
 constexpr int MAXSLAB = 8;      // TMEM: 8 x 32 columns of E accumulators
+constexpr int E_FLUSH_TILES = 32;  // the tensor core adds into fp32 accumulators with truncation: bound the chain length (bias ~1e-8 per MMA)
 constexpr int EPI_WARPS = 16;      // 4 lane quadrants x 4 snapshot quarters
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = 128 + EPI_THREADS;
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 G3_PLANE(0) G3_PLANE(1) G3_PLANE(2)
 #undef G3_PLANE
                 umma_commit(bar(W_EMPTY0 + buf));  // W slab is dead after G3: let the producer refill it while G4 runs
-                uint32_t acc = tl > 0 ? 1u : 0u;
+                uint32_t acc = (tl % E_FLUSH_TILES) > 0 ? 1u : 0u;  // fresh E accumulators after every flush
                 const uint32_t e_tmem = tmem + TMEM_E + slab * KP;
                 // G4: E^T += R^T G  (K = points: 8 k-steps of 16 rows = 2048 B; B = G_s K-major, box = ks / 4)
 #define G4_PAIR(PA, PB)                                                                                              \
@@ -350,6 +351,28 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             tmem_ld8(tmem + lane_addr + TMEM_D + KP + h * 8, v1);
             tmem_ld8(tmem + lane_addr + TMEM_D + 2 * KP + h * 8, v2);
             tmem_ld_wait();
+            if ((tile_local + 1) % E_FLUSH_TILES == 0 || tile_local == my_tiles - 1) {
+                // E^T accumulators -> this CTA's fp32 partial (round-to-nearest adds), then the MMA issuer restarts them at zero
+                const bool first = tile_local < E_FLUSH_TILES;
+                float* Eo = a.Epart + (long long)blockIdx.x * a.kp_out * a.mld;
+                for (int slab = h; slab < nslab; slab += NQ) {
+                    const int t = slab * BT + p;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t v[16];
+                        tmem_ld16(tmem + lane_addr + TMEM_E + slab * KP + c * 16, v);
+                        tmem_ld_wait();
+                        if (t < a.mld) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c * 16 + j < a.kp_out) {
+                                    float* dst = Eo + (long long)(c * 16 + j) * a.mld + t;
+                                    *dst = first ? __uint_as_float(v[j]) : *dst + __uint_as_float(v[j]);
+                                }
+                        }
+                    }
+                }
+            }
             tc_fence_before();
             mbar_arrive(bar(D_EMPTY));
 #pragma unroll
@@ -480,23 +503,6 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             for (int i = 0; i < 8; ++i) a.dbg[8192 + e * 8 + i] = te[i];
         // last tile's chain rule, then the E accumulators of this CTA
         if (my_tiles > 0) store_d(my_tiles - 1, blockIdx.x + (long long)(my_tiles - 1) * gridDim.x);
-        if (total > 0) mbar_wait(bar(R_EMPTY), (total - 1) & 1, 13, total);
-        tc_fence_after();
-        float* Eo = a.Epart + (long long)blockIdx.x * a.kp_out * a.mld;
-        for (int slab = h; slab < nslab; slab += NQ) {
-            const int t = slab * BT + p;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[16];
-                tmem_ld16(tmem + lane_addr + TMEM_E + slab * KP + c * 16, v);
-                tmem_ld_wait();
-                if (t < a.mld) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c * 16 + j < a.kp_out) Eo[(long long)(c * 16 + j) * a.mld + t] = __uint_as_float(v[j]);
-                }
-            }
-        }
         loss_acc = warp_sum(loss_acc);
         if (lane == 0) atomicAdd(&red_s[q * kScal + 0], loss_acc);
         tc_fence_before();
@@ -625,11 +631,6 @@ int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const flo
     reduce_partials_launch(ws.Epart, grid, (long long)Kp * s->mld, ws.Spart, grid + nchain, s->r, red, st);
     DESMO_CUDA(cudaGetLastError());
     return DESMO_OK;
-}
-
-int pod_gram_tc(const desmo_shape* s, const float* U, float* C, void* workspace, cudaStream_t st) {
-    (void)s; (void)U; (void)C; (void)workspace; (void)st;
-    return DESMO_ERR_UNSUPPORTED;
 }
 
 }  // namespace desmo

@@ -207,12 +207,19 @@ class DesmoEngine:
         Cm = torch.zeros(self.m, self.m, **f32)
         V, sigma = torch.zeros(self.r, self.m, **f32), torch.zeros(self.r, **f32)
         ws = torch.zeros(2 * 8 * 16 * self.m + 1024, dtype=torch.uint8, device=self.device)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         with torch.cuda.device(self.device):
+            ev[0].record()
             check(self.lib.desmo_pod_gram(C.byref(self.shape), _ptr(self.U), _ptr(Cm), _ptr(self.workspace), self._stream()), "desmo_pod_gram")
+            ev[1].record()
             if self.n_global != self.n and torch.distributed.is_initialized():
                 torch.distributed.all_reduce(Cm, group=self.pg)
             check(self.lib.desmo_pod_eig(self.m, self.r, _ptr(Cm), _ptr(V), _ptr(sigma), _ptr(ws), ws.numel(), self._stream()), "desmo_pod_eig")
+            ev[2].record()
             check(self.lib.desmo_pod_project(C.byref(self.shape), _ptr(self.U), _ptr(V), _ptr(sigma), _ptr(self.P), self._stream()),
                   "desmo_pod_project")
+            ev[3].record()
+        torch.cuda.synchronize(self.device)
+        self.pod_timing = {"gram_ms": ev[0].elapsed_time(ev[1]), "eig_ms": ev[1].elapsed_time(ev[2]), "project_ms": ev[2].elapsed_time(ev[3])}
         self.pod_V, self.pod_gram = V, Cm
         return sigma
