@@ -32,7 +32,7 @@ WORKLOADS = {
     "cylinder-fourier": (3961, 1001, 2, 2, 10),
     "channel-script": (16384, 1000, 4, 2, 0),
 }
-METRIC = "train_iters_per_s"
+METRIC = "train_iters_per_s"  # x slabs: one unit = one train iteration over one GPU-slab (weak scaling: N slabs per step at N GPUs)
 UNIT = "it/s"
 
 
@@ -163,7 +163,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        leg = cpu_reference_leg(n * world, m, r, p, nF, max(args.steps // 4, 3), 1, args.cpu_sample or None)
+        # unit of `value` (both arms): slab-iterations per second, a slab being one GPU's share (n points x m snapshots); the host
+        # cores process slabs at the same rate whatever N is, the GPUs process N of them per step (weak scaling)
+        leg = cpu_reference_leg(n, m, r, p, nF, max(args.steps // 4, 3), 1, args.cpu_sample or None)
         line = {"impl": "reference", "metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1000.0 / leg["value"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "cpu_baseline": leg,
