@@ -13,6 +13,7 @@ HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "desmo_b200.h")
 PATH_AUTO, PATH_FP32, PATH_TC = 0, 1, 2
 HYP_LR_GATES, HYP_LR_PHI, HYP_LR_Z, HYP_LR_OMEGA, HYP_LR_PERIOD, HYP_BETA, HYP_L1_LAMBDA, HYP_COUNT = range(8)
 MAX_R, MAX_P, MAX_K = 8, 7, 64
+PRE_MAGNITUDE, PRE_SUBTRACT_MEAN, PRE_SCALE_SQRT_M = 1, 2, 4
 
 
 class DesmoError(RuntimeError):
@@ -46,6 +47,7 @@ SIGNATURES: Dict[str, tuple] = {
     "desmo_pod_gram": (C.c_int, [_SP] + [_vp] * 4),
     "desmo_pod_eig": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "desmo_pod_project": (C.c_int, [_SP] + [_vp] * 5),
+    "desmo_preprocess": (C.c_int, [_SP, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "desmo_session_create": (C.c_int, [_i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
     "desmo_session_destroy": (C.c_int, [_vp]),
     "desmo_session_set_pod_host": (C.c_int, [_vp, _vp]),

@@ -64,6 +64,19 @@ int build_mono_table(int r, int p, MonoTable* mt) {
             for (int w = q; w < d; ++w) idx[w] = v;
         }
     }
+    // parent links: term (i1..id) -> term (i1..i_{d-1}); terms of one degree are contiguous and lexicographic
+    for (int t = 0; t < j; ++t) {
+        const int dgr = mt->deg[t];
+        mt->parent[t] = 0;
+        mt->last[t] = dgr ? mt->idx[t][dgr - 1] : 0;
+        if (dgr <= 1) continue;
+        for (int u = 0; u < t; ++u) {
+            if (mt->deg[u] != dgr - 1) continue;
+            bool same = true;
+            for (int q = 0; q < dgr - 1; ++q) same = same && (mt->idx[u][q] == mt->idx[t][q]);
+            if (same) { mt->parent[t] = (uint8_t)u; break; }
+        }
+    }
     return j;
 }
 
@@ -303,6 +316,27 @@ int desmo_pod_project(const desmo_shape* s, const float* U, const float* V, cons
     if ((rc = device_ok())) return rc;
     if (!U || !V || !sigma || !P) { set_error("desmo_pod_project: null pointer"); return DESMO_ERR_ARG; }
     return pod_project(s, U, V, sigma, P, (cudaStream_t)stream);
+}
+
+int desmo_preprocess(const desmo_shape* s, const void* V, int32_t v_dtype, int64_t v_ld, int32_t m_in, int32_t t_stride, int32_t d_in,
+                     int32_t d_use, int32_t flags, float* U, double* mean, void* stream) {
+    Dims d;
+    int rc = validate_shape(s, &d);
+    if (rc) return rc;
+    if (!V || !U) { set_error("desmo_preprocess: null pointer"); return DESMO_ERR_ARG; }
+    if (v_dtype != DESMO_DTYPE_F32 && v_dtype != DESMO_DTYPE_F64) { set_error("desmo_preprocess: v_dtype must be F32 or F64"); return DESMO_ERR_ARG; }
+    if (d_in < 1 || d_in > 3 || d_use < 1 || d_use > d_in) { set_error("desmo_preprocess: need 1 <= d_use <= d_in <= 3"); return DESMO_ERR_ARG; }
+    if (!(flags & DESMO_PRE_MAGNITUDE) && d_in != 1) {
+        set_error("desmo_preprocess: without DESMO_PRE_MAGNITUDE every component is its own row (pass n = points * d, d_in = 1)");
+        return DESMO_ERR_ARG;
+    }
+    if (t_stride < 1 || m_in < 1 || s->m != (m_in + t_stride - 1) / t_stride) {
+        set_error("desmo_preprocess: shape.m must equal ceil(m_in / t_stride)");
+        return DESMO_ERR_ARG;
+    }
+    if (v_ld < s->n * d_in) { set_error("desmo_preprocess: v_ld < n * d_in"); return DESMO_ERR_ARG; }
+    if ((rc = device_ok())) return rc;
+    return preprocess(s, V, v_dtype, v_ld, m_in, t_stride, d_in, d_use, flags, U, mean, (cudaStream_t)stream);
 }
 
 }  // extern "C"

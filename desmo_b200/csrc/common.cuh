@@ -22,6 +22,9 @@ constexpr int kMaxSlots = 2048;
 struct MonoTable {
     int8_t idx[kMaxT][kMaxP + 1];
     int8_t deg[kMaxT];
+    // L_j = L_parent[j] * Phi_last[j]  (the same left-to-right product as POOL_DATA): lets the chain rule run as one reverse sweep
+    uint8_t parent[kMaxT];
+    int8_t last[kMaxT];
 };
 
 struct Workspace {  // device-side carve-up of the caller's workspace; computed identically on the host
@@ -85,6 +88,8 @@ int pod_gram_fp32(const desmo_shape* s, const float* U, float* C, cudaStream_t s
 int pod_gram_tc(const desmo_shape* s, const float* U, float* C, void* workspace, cudaStream_t st);
 int pod_eig(int m, int r, const float* C, float* V, float* sigma, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int pod_project(const desmo_shape* s, const float* U, const float* V, const float* sigma, float* P, cudaStream_t st);
+int preprocess(const desmo_shape* s, const void* V, int v_dtype, long long v_ld, int m_in, int t_stride, int d_in, int d_use, int flags,
+               float* U, double* mean, cudaStream_t st);
 
 struct Dims { int T, K, Kp; MonoTable mt; };
 int validate_shape(const desmo_shape* s, Dims* d);

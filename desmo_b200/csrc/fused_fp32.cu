@@ -245,32 +245,61 @@ __global__ void __launch_bounds__(kTile, 1) fused_fp32_kernel(const FusedArgs a)
     }
 }
 
-// Chain rule for the chunked path: Dacc [Kp][ld] (unscaled) -> dphi, d omega, Phi^T Phi partials.
+// Chain rule: Dacc [Kp][ld] (raw dG = R W^T) -> dphi, d omega, Phi^T Phi partials.  Used by the chunked FFMA path and by the
+// tensor-core path.  The monomial part is ONE reverse sweep over the library: with L_j = L_parent(j) * Phi_last(j) (exactly the
+// left-to-right products of POOL_DATA, CYL:390-431), adj(L_parent) += adj(L_j) * Phi_last and dPhi_last += adj(L_j) * L_parent --
+// two FMAs per term instead of a product per (term, position).
 __global__ void __launch_bounds__(kTile) chain_rule_kernel(const FusedArgs a, int slot_base) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* red_s = reinterpret_cast<double*>(smem_raw);
     float* fs = reinterpret_cast<float*>(smem_raw + 8 * kScal * sizeof(double));
+    const int r = a.r, T = a.T, K = a.K;
     float* Phi_s = fs;                         // [kMaxR][kTile]
     float* dPhi_s = Phi_s + kMaxR * kTile;     // [kMaxR][kTile]
-    float* dom_s = dPhi_s + kMaxR * kTile;     // [3*kMaxR][kTile]
-    float* D_s = dom_s + 3 * kMaxR * kTile;    // [K][kTile]
+    float* L_s = dPhi_s + kMaxR * kTile;       // [T][kTile]   library values
+    float* A_s = L_s + T * kTile;              // [T][kTile]   adjoints, start as D_j
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int r = a.r, T = a.T, K = a.K;
     for (int i = tid; i < 8 * kScal; i += kTile) red_s[i] = 0.0;
     __syncthreads();
     const long long ntiles = (a.ld + kTile - 1) / kTile;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long x = tile * kTile + tid;
         const bool xin = x < a.n;
-        for (int i = 0; i < r; ++i)
+        for (int i = 0; i < r; ++i) {
             Phi_s[i * kTile + tid] = (x < a.ld) ? a.phi[(long long)i * a.ld + x] * a.P[(long long)i * a.ld + x] : 0.0f;
-        for (int j = 0; j < K; ++j) D_s[j * kTile + tid] = xin ? a.Dacc[(long long)j * a.ld + x] * a.scale : 0.0f;
-        chain_rule_point(a.mt, r, T, a.omega, Phi_s + tid, D_s + tid, dPhi_s + tid, dom_s + tid, kTile);
-        for (int i = 0; i < r; ++i)
-            if (x < a.ld) a.dphi[(long long)i * a.ld + x] = dPhi_s[i * kTile + tid] * a.P[(long long)i * a.ld + x];
-        for (int i = 0; i < 3 * r; ++i) {
-            const float v = warp_sum(xin ? dom_s[i * kTile + tid] : 0.0f);
-            if (lane == 0) red_s[warp * kScal + 1 + kMaxR * kMaxR + i] += (double)v;
+            dPhi_s[i * kTile + tid] = 0.0f;
+        }
+        L_s[tid] = 1.0f;
+        for (int j = 1; j < T; ++j) {
+            const float f = Phi_s[a.mt.last[j] * kTile + tid];
+            L_s[j * kTile + tid] = (a.mt.deg[j] == 1) ? f : L_s[a.mt.parent[j] * kTile + tid] * f;
+        }
+        for (int j = 0; j < T; ++j) A_s[j * kTile + tid] = xin ? a.Dacc[(long long)j * a.ld + x] * a.scale : 0.0f;
+        for (int j = T - 1; j >= 1; --j) {
+            const float adj = A_s[j * kTile + tid];
+            const int par = a.mt.parent[j], v = a.mt.last[j];
+            dPhi_s[v * kTile + tid] = fmaf(adj, L_s[par * kTile + tid], dPhi_s[v * kTile + tid]);
+            if (par > 0) A_s[par * kTile + tid] = fmaf(adj, Phi_s[v * kTile + tid], A_s[par * kTile + tid]);
+        }
+        for (int i = 0; i < r; ++i) {
+            const float ph = Phi_s[i * kTile + tid], pod = (x < a.ld) ? a.P[(long long)i * a.ld + x] : 0.0f;
+            const float ws = a.omega[3 * i], wc = a.omega[3 * i + 1], wh = a.omega[3 * i + 2];
+            float ds = 0.0f, dc = 0.0f, dh = 0.0f;
+            if (xin) {
+                ds = a.Dacc[(long long)(T + i) * a.ld + x] * a.scale;
+                dc = a.Dacc[(long long)(T + r + i) * a.ld + x] * a.scale;
+                dh = a.Dacc[(long long)(T + 2 * r + i) * a.ld + x] * a.scale;
+            }
+            const float cs = cosf(ws * ph), sn = sinf(wc * ph), th = tanhf(wh * ph);
+            const float sech2 = 1.0f - th * th;
+            const float dphi_i = dPhi_s[i * kTile + tid] + (ds * ws * cs - dc * wc * sn + dh * wh * sech2);
+            if (x < a.ld) a.dphi[(long long)i * a.ld + x] = dphi_i * pod;
+            const float o0 = warp_sum(ds * ph * cs), o1 = warp_sum(-dc * ph * sn), o2 = warp_sum(dh * ph * sech2);
+            if (lane == 0) {
+                red_s[warp * kScal + 1 + kMaxR * kMaxR + 3 * i] += (double)o0;
+                red_s[warp * kScal + 1 + kMaxR * kMaxR + 3 * i + 1] += (double)o1;
+                red_s[warp * kScal + 1 + kMaxR * kMaxR + 3 * i + 2] += (double)o2;
+            }
         }
         for (int i = 0; i < r; ++i)
             for (int j = i; j < r; ++j) {
@@ -278,6 +307,7 @@ __global__ void __launch_bounds__(kTile) chain_rule_kernel(const FusedArgs a, in
                 if (lane == 0) red_s[warp * kScal + 1 + i * kMaxR + j] += (double)v;
             }
     }
+    (void)K;
     __syncthreads();
     for (int i = tid; i < kScal; i += kTile) {
         double s = 0.0;
@@ -330,7 +360,7 @@ int chain_rule_launch(const desmo_shape* s, const MonoTable& mt, int T, int Kp, 
     a.mt = mt;
     const long long ntiles = (a.ld + kTile - 1) / kTile;
     const int gc = (int)(ntiles < 592 ? ntiles : 592);
-    const size_t sm = 8 * kScal * sizeof(double) + (size_t)(5 * kMaxR + a.K) * kTile * sizeof(float);
+    const size_t sm = 8 * kScal * sizeof(double) + (size_t)(2 * kMaxR + 2 * a.T) * kTile * sizeof(float);
     DESMO_CUDA(cudaFuncSetAttribute(chain_rule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     chain_rule_kernel<<<gc, kTile, sm, st>>>(a, slot_base);
     DESMO_CUDA(cudaGetLastError());
@@ -367,7 +397,7 @@ static int launch_fused(const FusedArgs& a, int sms, size_t smem_cap, cudaStream
     int nslots = gx * nchunk;
     if (nchunk > 1) {
         const int gc = (int)(ntiles < 256 ? ntiles : 256);
-        const size_t sm = 8 * kScal * sizeof(double) + (size_t)(5 * kMaxR + a.K) * kTile * sizeof(float);
+        const size_t sm = 8 * kScal * sizeof(double) + (size_t)(2 * kMaxR + 2 * a.T) * kTile * sizeof(float);
         DESMO_CUDA(cudaFuncSetAttribute(chain_rule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         chain_rule_kernel<<<gc, kTile, sm, st>>>(b, nslots);
         DESMO_CUDA(cudaGetLastError());

@@ -199,6 +199,27 @@ class DesmoEngine:
         return float(self.red[self.Kp * self.mld].item())
 
     # ------------------------------------------------------------------ POD (method of snapshots)
+    def preprocess_snapshot(self, raw: torch.Tensor, d_in: int = 1, d_use: Optional[int] = None, magnitude: bool = True,
+                            subtract_mean: bool = True, scale_sqrt_m: bool = False, t_stride: int = 1) -> torch.Tensor:
+        """Reader output -> resident snapshot U on the device (desmo_preprocess): magnitude of the first ``d_use`` of ``d_in``
+        velocity components (CYL:88-133), temporal-mean removal (CYL:136-149), optional 1/sqrt(m) (ANEU:143) and every
+        ``t_stride``-th snapshot (TURB:189).  ``raw`` is X.T as read: [m_in, n*d_in], fp32 or fp64, on this device.
+        Returns the fp64 temporal mean [n] (the reference's X_mean)."""
+        d_use = d_in if d_use is None else d_use
+        if raw.device != self.device or raw.dtype not in (torch.float32, torch.float64) or raw.dim() != 2 or raw.stride(1) != 1:
+            raise ValueError("raw must be a [m_in, n*d_in] fp32/fp64 tensor on the engine's device with unit inner stride")
+        if raw.shape[1] != self.n * d_in:
+            raise ValueError(f"raw has {raw.shape[1]} columns, expected n*d_in = {self.n * d_in}")
+        if self.U is None:
+            self.U = torch.empty(self.m, self.ld, dtype=torch.float32, device=self.device)
+        mean = torch.empty(self.n, dtype=torch.float64, device=self.device)
+        flags = (_lib.PRE_MAGNITUDE if magnitude else 0) | (_lib.PRE_SUBTRACT_MEAN if subtract_mean else 0) | \
+                (_lib.PRE_SCALE_SQRT_M if scale_sqrt_m else 0)
+        _lib.check(self.lib.desmo_preprocess(C.byref(self.shape), raw.data_ptr(), 1 if raw.dtype == torch.float64 else 0, raw.stride(0),
+                                             raw.shape[0], t_stride, d_in, d_use, flags, self.U.data_ptr(), mean.data_ptr(),
+                                             self._stream()), "desmo_preprocess")
+        return mean
+
     def pod_from_snapshot(self) -> torch.Tensor:
         """Replaces POD_analysis (CYL:197-205) for the resident snapshot matrix: returns singular values (r,), fills self.P."""
         if self.U is None:

@@ -97,6 +97,37 @@ class DesmoTrainer:
         self.epoch += 1
         return out
 
+    # ---- checkpoint / resume.  The reference saves only model.state_dict() (CYL:781-786,802-805): no
+    # optimizer / scheduler state and no POD modes, so its checkpoints cannot resume a run.  `model.state_dict()` stays the
+    # reference-compatible artefact; this adds everything else needed for an exact continuation.
+    def state_dict(self) -> dict:
+        e = self.engine
+        opt = {k: getattr(e, k).detach().clone() for k in ("phi_m", "phi_u", "gates_m", "gates_u", "rows_m", "rows_u", "omega_m", "omega_u",
+                                                           "coefs_m", "coefs_u", "periods_m", "periods_u") if getattr(e, k) is not None}
+        return {"model": {k: v.detach().clone() for k, v in self.model.state_dict().items()} if hasattr(self.model, "state_dict") else None,
+                "optimizer": opt, "step": int(e.step_dev.item()), "pod_modes": e.P[:, :e.n].detach().clone(),
+                "scheduler": {"lrs": list(self.scheduler.lrs), "best": self.scheduler.best, "num_bad": self.scheduler.num_bad,
+                              "patience": self.scheduler.patience},
+                "epoch": self.epoch, "beta": self.beta, "l1_lambda": self.l1_lambda, "sched_every": self.sched_every,
+                "shape": {"n": e.n, "m": e.m, "r": e.r, "polyorder": e.polyorder, "nF": e.nF, "n_global": e.n_global}}
+
+    def load_state_dict(self, sd: dict) -> None:
+        e = self.engine
+        shp = sd["shape"]
+        if (shp["n"], shp["m"], shp["r"], shp["polyorder"], shp["nF"]) != (e.n, e.m, e.r, e.polyorder, e.nF):
+            raise ValueError(f"checkpoint shape {shp} does not match the engine")
+        if sd.get("model") is not None and hasattr(self.model, "load_state_dict"):
+            self.model.load_state_dict(sd["model"], strict=True)
+        for k, v in sd["optimizer"].items():
+            getattr(e, k).copy_(v)
+        e.step_dev.fill_(int(sd["step"]))
+        e.P.zero_()
+        e.P[:, :e.n].copy_(sd["pod_modes"])
+        sc = sd["scheduler"]
+        self.scheduler.lrs, self.scheduler.best, self.scheduler.num_bad = list(sc["lrs"]), sc["best"], sc["num_bad"]
+        self.epoch, self.beta, self.l1_lambda = int(sd["epoch"]), float(sd["beta"]), float(sd["l1_lambda"])
+        e.set_hyper(self.scheduler.lrs, self.beta, self.l1_lambda)
+
     def fit(self, snapshot: torch.Tensor, epochs: int, log_every: int = 0):
         self.engine.set_snapshot(snapshot)
         for _ in range(epochs):

@@ -47,7 +47,7 @@ extern "C" {
 
 #define DESMO_PATH_AUTO 0
 #define DESMO_PATH_FP32 1  /* FFMA path */
-#define DESMO_PATH_TC 2    /* tcgen05 3xTF32 path */
+#define DESMO_PATH_TC 2    /* tcgen05 path, 3-way bf16 split (fp32-grade accuracy) */
 
 typedef struct desmo_shape {
     int64_t n;        /* mesh points owned by this rank (rows of the reference's X) */
@@ -134,6 +134,20 @@ int desmo_pod_gram(const desmo_shape* s, const float* U, float* C, void* workspa
 int desmo_pod_eig(int32_t m, int32_t r, const float* C, float* V, float* sigma, void* workspace, size_t workspace_bytes,
                   void* stream);
 int desmo_pod_project(const desmo_shape* s, const float* U, const float* V, const float* sigma, float* P, void* stream);
+
+/* Snapshot pre-processing between the reader and POD/training, on the device (reference: numpy on the host).  V is X.T as
+ * read: V[m_in][v_ld] with v_ld >= n * d_in, a point's d_in components adjacent.  Replaces convert3Dto2D_data (CYL:88-106:
+ * d_in = 3, d_use = 2), convertToMagnitude (CYL:109-133, float64), subtract_mean (CYL:136-149; mean over all m_in snapshots),
+ * the aneurysm scripts' 1/sqrt(m) scaling (ANEU:143), the channel script's X[:,0::2] (TURB:189: t_stride = 2, s->m =
+ * ceil(m_in / t_stride)) and the X.T -> FloatTensor cast (CYL:356,708).  Output U[s->m][s->ld] (pad columns zeroed) and,
+ * if mean != NULL, the fp64 temporal mean[n] (X_mean). */
+#define DESMO_DTYPE_F32 0
+#define DESMO_DTYPE_F64 1
+#define DESMO_PRE_MAGNITUDE 1
+#define DESMO_PRE_SUBTRACT_MEAN 2
+#define DESMO_PRE_SCALE_SQRT_M 4
+int desmo_preprocess(const desmo_shape* s, const void* V, int32_t v_dtype, int64_t v_ld, int32_t m_in, int32_t t_stride,
+                     int32_t d_in, int32_t d_use, int32_t flags, float* U, double* mean, void* stream);
 
 /* Device-resident training session fed from HOST memory (one process of the reference's loop, CYL:706-778).
  * desmo_session_step_host(snapshot_host) = `snapshot = x[0].type(FloatTensor).to(device)` (CYL:708, pass NULL to keep the

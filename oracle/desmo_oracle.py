@@ -512,6 +512,33 @@ def subtract_mean(X: np.ndarray) -> np.ndarray:
     return X - X.mean(axis=1, keepdims=True)
 
 
+def preprocess(X_raw: np.ndarray, d_in: int, d_use: int, magnitude: bool = True, subtract: bool = True, scale_sqrt_m: bool = False,
+               t_stride: int = 1):
+    """The reference's numpy pre-processing between the reader and POD/training, float64 throughout.
+
+    X_raw is the reader's matrix (n*d_in rows x m_in snapshots, the d_in components of a point on adjacent rows, CYL:52-85).
+    convert3Dto2D_data drops every third row (CYL:88-106; d_in=3, d_use=2); convertToMagnitude takes sqrt(sum(square)) over
+    the d_use components of each point (CYL:109-133); subtract_mean removes the temporal mean of every row (CYL:136-149) and,
+    in the aneurysm scripts, multiplies by 1/sqrt(m) (ANEU:130-144); the channel script then keeps every second snapshot
+    (TURB:189, after the mean).  Returns (X, X_mean) with X (n x ceil(m_in/t_stride)) float64 -- the training snapshot is
+    X.T cast to float32 (CYL:356,708)."""
+    X = np.asarray(X_raw, np.float64)
+    if d_use != d_in:
+        keep = [i for i in range(X.shape[0]) if i % d_in < d_use]
+        X = X[keep]
+    if magnitude:
+        n = X.shape[0] // d_use
+        X = np.sqrt(np.sum(np.square(X.reshape(n, d_use, X.shape[1])), axis=1))
+    elif d_use != 1:
+        raise ValueError("without magnitude every component is its own row: pass d_in = d_use = 1")
+    m_in = X.shape[1]
+    X_mean = np.mean(X, 1) if subtract else np.zeros(X.shape[0])
+    X = X - X_mean[:, None]
+    if scale_sqrt_m:
+        X = (1 / np.sqrt(m_in)) * X
+    return np.ascontiguousarray(X[:, 0::t_stride]), X_mean
+
+
 def synthetic_snapshots(kind: str, n: int, m: int, seed: int = 0) -> np.ndarray:
     """fp64 (n, m) data matrix X with the reference's pre-processing applied.
 

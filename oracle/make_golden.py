@@ -78,9 +78,59 @@ def grads_packed(model, params):
     return out
 
 
+ANEU = "DESMO/aneurysm/DESMO_ICA_norm.py"
+TURB = "DESMO/turbulent_channel/DESMO-TurbulentChannel.py"
+
+
+def raw_velocity(n: int, m: int, d: int, seed: int) -> np.ndarray:
+    """Reader-shaped input (n*d rows x m snapshots, components of a point on adjacent rows, CYL:52-85); fp32-representable
+    values so that the fp32 and fp64 device inputs see the same numbers.  For d = 3 the w rows are NOT zero: the reference
+    drops them regardless."""
+    rng = np.random.default_rng(seed)
+    t = np.linspace(0.0, 6.0, m)
+    base = rng.standard_normal((n * d, 1)) + 0.6 * rng.standard_normal((n * d, 1)) * np.sin(t)[None, :] \
+        + 0.3 * rng.standard_normal((n * d, 1)) * np.cos(2.3 * t)[None, :] + 0.05 * rng.standard_normal((n * d, m))
+    return base.astype(np.float32).astype(np.float64)
+
+
+def preprocess_golden():
+    """Runs the reference's own convert3Dto2D_data / convertToMagnitude / subtract_mean (three script variants)."""
+    fx = {}
+    cyl = ref.load_definitions(ref.CYL, ("convert3Dto2D_data", "convertToMagnitude", "subtract_mean"), {})
+    aneu = ref.load_definitions(ANEU, ("convertToMagnitude", "subtract_mean"), {})
+    # CYL:170-191 -- 2-D flow stored with 3 components: drop w, magnitude over (u, v), subtract the mean
+    X = raw_velocity(301, 37, 3, 11)
+    fx["cyl_raw"] = X.copy()
+    Y = cyl["convertToMagnitude"](cyl["convert3Dto2D_data"](X.copy()), 2)
+    Y, mean = cyl["subtract_mean"](Y)
+    fx["cyl_X"], fx["cyl_mean"] = Y, mean
+    # ANEU:165-176 -- 3-D flow: magnitude over (u, v, w), subtract the mean, scale by 1/sqrt(m)
+    X = raw_velocity(257, 50, 3, 12)
+    fx["aneu_raw"] = X.copy()
+    Y, mean = aneu["subtract_mean"](aneu["convertToMagnitude"](X.copy()))
+    fx["aneu_X"], fx["aneu_mean"] = Y, mean
+    # TURB:170-189 -- 3-D magnitude, subtract the mean, then keep every second snapshot
+    turb = ref.load_definitions(TURB, ("convertToMagnitude", "subtract_mean"), {})
+    X = raw_velocity(192, 41, 3, 13)
+    fx["turb_raw"] = X.copy()
+    Y, mean = turb["subtract_mean"](turb["convertToMagnitude"](X.copy(), 3))
+    fx["turb_X"], fx["turb_mean"] = Y[:, 0::2], mean
+    # convertToMagnitude_flag = False (CYL:171): the components stay separate rows, only the mean is removed
+    X = raw_velocity(100, 29, 2, 14)
+    fx["vec_raw"] = X.copy()
+    Y, mean = cyl["subtract_mean"](X.copy())
+    fx["vec_X"], fx["vec_mean"] = Y, mean
+    fx = {k: (v.astype(np.float32) if k.endswith("_raw") else v) for k, v in fx.items()}  # raw values are fp32-exact by construction
+    np.savez_compressed(os.path.join(OUT, "preprocess.npz"), **fx)
+    print("preprocess.npz", {k: v.shape for k, v in fx.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(4)
+    preprocess_golden()
+    if "--only-preprocess" in sys.argv:
+        return
     facts = {"T": {}, "param_totals": {}, "checkpoints": {}}
     for (r, p) in [(4, 3), (4, 2), (2, 2), (8, 3), (8, 2), (32, 2), (3, 4), (2, 7)]:
         ns = ref.load_definitions(ref.CYL, ("binomial_coefficient", "calculate_number_of_terms"), {})

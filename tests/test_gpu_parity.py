@@ -337,3 +337,64 @@ def test_tensor_core_path_matches_ffma_path_at_scale():
     assert rel(d2, d1) < 1e-5 and rel(r2[ec + 17:], r1[ec + 17:]) < 1e-5   # d phi, d omega
     bias = float(((r2[:ec] - r1[:ec]) * np.sign(r1[:ec])).sum() / np.abs(r1[:ec]).sum())
     assert abs(bias) < 5e-6, bias
+
+
+def test_checkpoint_resume_is_exact(tmp_path):
+    """Trainer checkpoint (weights in the reference key layout + Adamax moments, step, scheduler, POD modes): 40 steps straight ==
+    20 steps, save, fresh objects, load, 20 steps -- bit for bit."""
+    from desmo_b200 import DESMO, DesmoTrainer
+
+    _, modes, snap, prm = make_case("cylinder", 600, 64, 4, 2, omega_init=10.0, perturb_rel=0.02)
+    lrs = (1e-2, 1e-3, 1e-2, 1e-2)
+    dev = torch.device("cuda:0")
+
+    def fresh():
+        model = DESMO(prm.n, prm.m, 2, 4, 10.0, pod_modes=modes, device=dev)
+        load_engine(model.engine, prm, modes, snap)
+        return model, DesmoTrainer(model, lrs=lrs, patience=2, sched_every=5, use_cuda_graph=False)
+
+    m1, t1 = fresh()
+    for _ in range(40):
+        t1.step()
+    m2, t2 = fresh()
+    for _ in range(20):
+        t2.step()
+    path = os.path.join(tmp_path, "ckpt.pt")
+    torch.save(t2.state_dict(), path)
+    m3, t3 = fresh()
+    m3.engine.P.zero_()  # the checkpoint must restore the POD modes too (the reference's .pt files do not carry them)
+    t3.load_state_dict(torch.load(path, map_location=dev, weights_only=False))
+    for _ in range(20):
+        t3.step()
+    torch.cuda.synchronize()
+    for k, v in engine_params(m1.engine).items():
+        assert np.array_equal(v, engine_params(m3.engine)[k]), k
+    assert t1.scheduler.lrs == t3.scheduler.lrs and t1.epoch == t3.epoch
+    assert list(torch.load(path, weights_only=False)["model"].keys()) == list(m1.state_dict().keys())
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("name,cfg", [("cyl", (3, 2, True, False, 1)), ("aneu", (3, 3, True, True, 1)), ("turb", (3, 3, True, False, 2)),
+                                      ("vec", (1, 1, False, False, 1))])
+def test_device_preprocess_matches_reference_golden(name, cfg, dtype):
+    """desmo_preprocess against the reference's own convert3Dto2D_data / convertToMagnitude / subtract_mean outputs (fixture
+    made by oracle/make_golden.py): the fp32 snapshot must be the float64 result rounded once (<= 1 ulp where the fp64
+    summation order of the mean moves a tie; > 99.9 % of the entries identical), the mean to 1e-13."""
+    from desmo_b200.engine import DesmoEngine
+
+    d_in, d_use, mag, scale, stride = cfg
+    fx = np.load(os.path.join(GOLDEN, "preprocess.npz"))
+    want = np.ascontiguousarray(fx[name + "_X"].T).astype(np.float32)  # CYL:356,708
+    m, n = want.shape
+    raw = torch.from_numpy(np.ascontiguousarray(fx[name + "_raw"].T)).to("cuda:0", getattr(torch, dtype))
+    e = DesmoEngine(n, m, 2, 2, device="cuda:0", path=1)
+    mean = e.preprocess_snapshot(raw, d_in=d_in, d_use=d_use, magnitude=mag, scale_sqrt_m=scale, t_stride=stride)
+    got = e.U[:, :n].cpu().numpy()
+    assert np.all(e.U[:, n:].cpu().numpy() == 0.0)
+    ulp = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 1 and (ulp == 0).mean() > 0.999, (int(ulp.max()), float((ulp == 0).mean()))
+    assert np.allclose(mean.cpu().numpy(), fx[name + "_mean"], rtol=1e-13, atol=1e-15)
+    # the pre-processed snapshot feeds POD directly: same singular values as the oracle's SVD of the reference's X
+    sig = e.pod_from_snapshot()
+    _, _, s_ref, _ = orc.pod_analysis(fx[name + "_X"], 2)
+    assert rel(sig.cpu().numpy()[:2], s_ref[:2]) < 1e-4

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import desmo_oracle as orc
+from tests.helpers import GOLDEN
 
 
 def rel(a, b):
@@ -153,3 +154,17 @@ def test_scheduler_and_adamax_match_torch():
         for k in tp:
             assert np.allclose(getattr(prm, k), tp[k].detach().numpy(), rtol=2e-6, atol=1e-7), (it, k)
     assert abs(opt.lrs[1] - 1e-6) < 1e-15  # phi group hits the floor first (DESMO/aneurysm/DESMO.out:4369-4371)
+
+
+PRE_CASES = {  # name -> (d_in, d_use, magnitude, scale_sqrt_m, t_stride)
+    "cyl": (3, 2, True, False, 1), "aneu": (3, 3, True, True, 1), "turb": (3, 3, True, False, 2), "vec": (1, 1, False, False, 1)}
+
+
+@pytest.mark.parametrize("name", sorted(PRE_CASES))
+def test_preprocess_matches_reference_golden(name):
+    """convert3Dto2D_data / convertToMagnitude / subtract_mean of CYL, ANEU and TURB, run by oracle/make_golden.py."""
+    fx = np.load(os.path.join(GOLDEN, "preprocess.npz"))
+    d_in, d_use, mag, scale, stride = PRE_CASES[name]
+    X, mean = orc.preprocess(fx[name + "_raw"].astype(np.float64), d_in, d_use, mag, True, scale, stride)
+    assert X.shape == fx[name + "_X"].shape
+    assert np.array_equal(X, fx[name + "_X"]) and np.array_equal(mean, fx[name + "_mean"])
