@@ -7,7 +7,7 @@ import re
 from typing import Dict, List
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdesmo_b200.so")
+LIB_PATH = os.environ.get("DESMO_B200_LIB") or os.path.join(HERE, "libdesmo_b200.so")  # override: kernel experiments (tools/variant.sh)
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "desmo_b200.h")
 
 PATH_AUTO, PATH_FP32, PATH_TC = 0, 1, 2

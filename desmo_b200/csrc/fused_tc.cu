@@ -16,6 +16,8 @@
 #include <string.h>
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace desmo {
@@ -43,11 +45,17 @@ constexpr uint32_t G_OFF = W_OFF + 2 * W_SLAB;         // 147456
 // Private rings matter: mbarrier parity waits are only sound if a waiter is never two phases away from the barrier, which a
 // ring shared by independently progressing consumer groups cannot guarantee.
 constexpr uint32_t U_OFF = G_OFF + 3 * G_PLANE;        // 172032
-constexpr int U_ROWS = 8;
-constexpr uint32_t U_STAGE = U_ROWS * BP * 4;          // 4096
+#ifndef DESMO_U_ROWS
+#define DESMO_U_ROWS 8
+#endif
+constexpr int U_ROWS = DESMO_U_ROWS;  // snapshots per TMA stage
+constexpr uint32_t U_STAGE = U_ROWS * BP * 4;          // 4096 (must be a multiple of 128 B, the TMA destination alignment)
 constexpr int U_STAGES = 3;                            // per quarter
+constexpr int U_TAIL = QT - U_STAGES * U_ROWS;         // snapshots of a quarter fetched by the epilogue threads themselves (registers)
 constexpr uint32_t RED_OFF = U_OFF + NQ * U_STAGES * U_STAGE;  // 221184  (4 quadrants x kScal doubles)
 constexpr uint32_t SMEM_BYTES = RED_OFF + 4 * kScal * 8 + 1024;  // + alignment slack
+static_assert(SMEM_BYTES + 1024 <= 232448, "dynamic + static shared memory must fit the 227 KB of an sm_100 CTA");
+static_assert(U_TAIL >= 0 && U_STAGE % 128 == 0, "U stage shape");
 constexpr uint32_t TMEM_REC = 0, TMEM_D = 128, TMEM_E = 256;  // D: 3 column blocks of 32 (N-stacked B planes), summed in the epilogue
 }  // namespace tc
 
@@ -151,12 +159,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // x = b1 + b2 + b3 (bf16 each, round-to-nearest): packs two consecutive elements (lo = first) per 32-bit word
+// (the conversions are `volatile` so that the compiler cannot sink them below the mbarrier wait that follows them in the epilogue)
 __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w1) : "f"(x1), "f"(x0));
+    asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w1) : "f"(x1), "f"(x0));
     const float e0 = x0 - __uint_as_float(w1 << 16), e1 = x1 - __uint_as_float(w1 & 0xffff0000u);
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w2) : "f"(e1), "f"(e0));
+    asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w2) : "f"(e1), "f"(e0));
     const float f0 = e0 - __uint_as_float(w2 << 16), f1 = e1 - __uint_as_float(w2 & 0xffff0000u);
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w3) : "f"(f1), "f"(f0));
+    asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w3) : "f"(f1), "f"(f0));
 }
 
 // The six (a-plane, b-plane) products kept by the 3-way split (i + j <= 4), smallest contributions first.
@@ -171,14 +180,15 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                                                                           const __grid_constant__ CUtensorMap tmU) {
     using namespace tc;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[40];
+    __shared__ __align__(8) uint64_t bars[44];
     __shared__ uint32_t tmem_base_s;
+    __shared__ uint32_t sink_s[32];  // write-only (see the epilogue)
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     double* red_s = reinterpret_cast<double*>(smem + RED_OFF);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     enum { W_FULL0 = 0, W_FULL1, W_EMPTY0, W_EMPTY1, REC_FULL, REC_EMPTY, R_FULL, R_EMPTY, G_FULL, G_EMPTY, D_FULL, D_EMPTY,
-           U_FULL0, U_EMPTY0 = U_FULL0 + NQ * U_STAGES };
+           U_FULL0, U_EMPTY0 = U_FULL0 + NQ * U_STAGES, R_EMPTYQ0 = U_EMPTY0 + NQ * U_STAGES };
     auto bar = [&](int i) { return smem_u32(&bars[i]); };
     auto mbar_wait = [&](uint32_t b, uint32_t parity, int tag = 0, int iter = 0) { mbar_wait_t<kDebug>(b, parity, tag, iter); };
     auto now = [&]() -> long long { return kDebug ? clock64() : 0ll; };
@@ -193,6 +203,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         mbar_init(bar(REC_FULL), 1); mbar_init(bar(REC_EMPTY), EPI_THREADS); mbar_init(bar(R_FULL), EPI_THREADS); mbar_init(bar(R_EMPTY), 1);
         mbar_init(bar(G_FULL), EPI_THREADS); mbar_init(bar(G_EMPTY), 1); mbar_init(bar(D_FULL), 1); mbar_init(bar(D_EMPTY), EPI_THREADS);
         for (int i = 0; i < NQ * U_STAGES; ++i) { mbar_init(bar(U_FULL0 + i), 1); mbar_init(bar(U_EMPTY0 + i), 128); }
+        for (int i = 0; i < 4; ++i) mbar_init(bar(R_EMPTYQ0 + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -219,9 +230,9 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         }
     } else if (warp == 3 || warp == 2) {
         // ================= TMA producers: U chunks [8 snapshots][128 points]; each thread feeds the private rings of two quarters ==========
-        // A ring holds the first 24 of a quarter's 32 snapshots (3 stages = exactly one slab-tile), so the three boxes of the NEXT
-        // slab-tile are requested as soon as the current ones are consumed; the last 8 snapshots are fetched by the epilogue threads
-        // themselves one slab ahead (registers).  No divisions in the loop: one thread sustains ~1 TMA instruction per 400 cycles.
+        // A ring holds the first 24 of a quarter's 32 snapshots (3 stages of 8 = exactly one slab-tile), so the three boxes of the
+        // NEXT slab-tile are requested as soon as the current ones are consumed; the last 8 snapshots are fetched by the epilogue
+        // threads themselves one slab ahead (registers).  (Stages of 9 rows also fit the 227 KB but measured 3 % slower.)  No divisions in the loop: one thread sustains ~1 TMA instruction per 400 cycles.
         if (elect_one_sync()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmU) : "memory");
             const int h0 = (warp - 2) * 2;
@@ -239,8 +250,12 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                         long long cp0 = now();
                         if (it > 0) mbar_wait(bar(U_EMPTY0 + st), par, 2, it);
                         tp0 += now() - cp0;
+#ifdef EXP_NO_UTMA
+                        mbar_arrive(bar(U_FULL0 + st));
+#else
                         mbar_expect_tx(bar(U_FULL0 + st), U_STAGE);
                         tma_load_2d(sbase + U_OFF + st * U_STAGE, &tmU, (int)(tile * BP), slab * BT + (h0 + hh) * QT + k * U_ROWS, bar(U_FULL0 + st));
+#endif
                     }
                 par ^= 1;
                 if (++slab == nslab) { slab = 0; tile += gridDim.x; }
@@ -273,7 +288,9 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                  desc_from(wa_lo + ((PB * W_PLANE + ks * 2048) >> 4), kDescHi), idesc_g1, acc);                       \
         acc = 1;                                                                                                      \
     }
+#ifndef EXP_NO_G1
                 DESMO_PAIRS(G1_PAIR)
+#endif
 #undef G1_PAIR
                 umma_commit(bar(REC_FULL));
             };
@@ -300,21 +317,32 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                  (PA == 0) ? acc0 : 1u);                                                                              \
         if (PA == 0) acc0 = 1;                                                                                        \
     }
+#ifndef EXP_NO_G3
                 G3_PLANE(0) G3_PLANE(1) G3_PLANE(2)
+#endif
 #undef G3_PLANE
                 umma_commit(bar(W_EMPTY0 + buf));  // W slab is dead after G3: let the producer refill it while G4 runs
                 uint32_t acc = (tl % E_FLUSH_TILES) > 0 ? 1u : 0u;  // fresh E accumulators after every flush
                 const uint32_t e_tmem = tmem + TMEM_E + slab * KP;
-                // G4: E^T += R^T G  (K = points: 8 k-steps of 16 rows = 2048 B; B = G_s K-major, box = ks / 4)
+                // G4: E^T += R^T G  (K = points: 8 k-steps of 16 rows = 2048 B; B = G_s K-major, box = ks / 4).  Issued lane quadrant
+                // by lane quadrant (k-steps 2q, 2q+1 read the R_s rows of points 32q..32q+31 only) with one commit each: the epilogue
+                // warps of quadrant q may overwrite their rows of R_s while G4 still works on the later quadrants, so only the LAST
+                // quadrant's stores (a quarter of the volume) are serialised between G4 of this slab and G3 of the next.
 #define G4_PAIR(PA, PB)                                                                                              \
-    _Pragma("unroll") for (int ks = 0; ks < BP / 16; ++ks) {                                                          \
+    _Pragma("unroll") for (int kk = 0; kk < 2; ++kk) {                                                                \
+        const int ks = 2 * qq + kk;                                                                                   \
         mma_bf16(e_tmem, desc_from(rm_lo + ((PA * R_PLANE + ks * 2048) >> 4), kDescHi),                                \
                  desc_from(gk_lo + ((PB * G_PLANE + (ks >> 2) * (KP * 128) + (ks & 3) * 32) >> 4), kDescHi), idesc_g4, acc); \
         acc = 1;                                                                                                      \
     }
-                DESMO_PAIRS(G4_PAIR)
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+#ifndef EXP_NO_G4
+                    DESMO_PAIRS(G4_PAIR)
+#endif
+                    umma_commit(bar(R_EMPTYQ0 + qq));
+                }
 #undef G4_PAIR
-                umma_commit(bar(R_EMPTY));
                 if (slab == nslab - 1) {
                     umma_commit(bar(D_FULL));
                     umma_commit(bar(G_EMPTY));
@@ -381,58 +409,72 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                     a.Dacc[(long long)(h * 8 + j) * a.ld + x] = (__uint_as_float(v2[j]) + __uint_as_float(v1[j])) + __uint_as_float(v0[j]);
         };
 
+        // ---- library row of a point (CYL:538-548,565-567).  The four quarters share the work (quarter h takes library terms
+        //      j = h, h+4, ...).  eval_library(next tile) runs while G3/G4 of the current tile's last slab occupy the tensor pipe,
+        //      so only the split + 24 two-byte stores sit between "G_s free" and "G_s full" at a tile boundary.  Rolled loops on
+        //      purpose (gv[] lives in local memory): this runs once per tile and straight-line code only thrashes the I-cache. ----
+        float gv[KP / NQ];
+        auto eval_library = [&](long long tile_) {
+            const long long x_ = tile_ * BP + p;
+            for (int i = 0; i < a.r; ++i) lat[i] = a.phi[(long long)i * a.ld + x_] * a.P[(long long)i * a.ld + x_];
+#pragma unroll 1
+            for (int jj = 0; jj < KP / NQ; ++jj) {
+                const int j = h + jj * NQ;
+                float v = 0.0f;
+                if (j < a.T) {
+                    v = monomial(a.mt, j, lat, 1);
+                } else if (j < a.K) {
+                    const int b = (j - a.T) / a.r, i = (j - a.T) - b * a.r;
+                    const float arg = a.omega[3 * i + b] * lat[i];
+                    v = (b == 0) ? sinf(arg) : (b == 1) ? cosf(arg) : tanhf(arg);
+                }
+                gv[jj] = v;
+            }
+        };
+        auto store_library = [&]() {  // three bf16 planes, G_s[lib rows][p contiguous]
+            const uint32_t gs = sbase + G_OFF + (p >> 6) * (KP * 128);
+            const uint32_t pb = (p & 63) * 2;
+#pragma unroll
+            for (int jj = 0; jj < KP / NQ; ++jj) {
+                const float v = gv[jj];
+                const __nv_bfloat16 b1 = __float2bfloat16_rn(v);
+                const float e1 = v - __bfloat162float(b1);
+                const __nv_bfloat16 b2 = __float2bfloat16_rn(e1);
+                const __nv_bfloat16 b3 = __float2bfloat16_rn(e1 - __bfloat162float(b2));
+                const uint32_t off = sw128(h + jj * NQ, pb);
+                st_shared_u16(gs + off, __bfloat16_as_ushort(b1));
+                st_shared_u16(gs + G_PLANE + off, __bfloat16_as_ushort(b2));
+                st_shared_u16(gs + 2 * G_PLANE + off, __bfloat16_as_ushort(b3));
+            }
+            fence_async_smem();
+            mbar_arrive(bar(G_FULL));
+        };
+
         int it = 0;
         for (int tl = 0; tl < my_tiles; ++tl) {
             const long long tile = blockIdx.x + (long long)tl * gridDim.x;
             const long long x = tile * BP + p;
             const bool xin = x < a.n;
             long long cg0 = now();
-            {
-                // ---- library row of this point (CYL:538-548,565-567), split into bf16 planes, G_s[lib rows][p contiguous].
-                //      The four quarters share the work (quarter h takes library terms j = h, h+4, ...).  Rolled loops on purpose:
-                //      this runs once per tile, and straight-line code here only thrashes the I-cache. ----
-                for (int i = 0; i < a.r; ++i) lat[i] = a.phi[(long long)i * a.ld + x] * a.P[(long long)i * a.ld + x];
-                long long cg1 = now();
-                if (tl > 0) mbar_wait(bar(G_EMPTY), (tl - 1) & 1, 9, tl);
-                cg0 = now(); te[5] += cg0 - cg1;
-                const uint32_t gs = sbase + G_OFF + (p >> 6) * (KP * 128);
-                const uint32_t pb = (p & 63) * 2;
-#pragma unroll 1
-                for (int j = h; j < KP; j += NQ) {
-                    float v = 0.0f;
-                    if (j < a.T) {
-                        v = monomial(a.mt, j, lat, 1);
-                    } else if (j < a.K) {
-                        const int b = (j - a.T) / a.r, i = (j - a.T) - b * a.r;
-                        const float arg = a.omega[3 * i + b] * lat[i];
-                        v = (b == 0) ? sinf(arg) : (b == 1) ? cosf(arg) : tanhf(arg);
-                    }
-                    const __nv_bfloat16 b1 = __float2bfloat16_rn(v);
-                    const float e1 = v - __bfloat162float(b1);
-                    const __nv_bfloat16 b2 = __float2bfloat16_rn(e1);
-                    const __nv_bfloat16 b3 = __float2bfloat16_rn(e1 - __bfloat162float(b2));
-                    const uint32_t off = sw128(j, pb);
-                    st_shared_u16(gs + off, __bfloat16_as_ushort(b1));
-                    st_shared_u16(gs + G_PLANE + off, __bfloat16_as_ushort(b2));
-                    st_shared_u16(gs + 2 * G_PLANE + off, __bfloat16_as_ushort(b3));
-                }
-                fence_async_smem();
-                mbar_arrive(bar(G_FULL));
-                te[6] += now() - cg0;
-            }
+            if (tl == 0) eval_library(tile);
+            long long cg1 = now();
+            if (tl > 0) mbar_wait(bar(G_EMPTY), (tl - 1) & 1, 9, tl);
+            cg0 = now(); te[5] += cg0 - cg1;
+            store_library();
+            te[6] += now() - cg0;
             if (tl > 0) store_d(tl - 1, tile - gridDim.x);
 
             float lsum = 0.0f;  // fp32 over the 256 residuals of a tile, folded into the fp64 accumulator once per tile (FP64 adds are slow)
-            float ulast[U_ROWS];
+            float ulast[U_TAIL];
             auto load_last = [&](int slab2) {  // snapshots 24..31 of this thread's quarter, straight from HBM/L2
-                const int tb = slab2 * BT + h * QT + 3 * U_ROWS;
+                const int tb = slab2 * BT + h * QT + U_STAGES * U_ROWS;
                 const float* up = a.U + (long long)tb * a.ld + x;
-                if (xin && tb + U_ROWS <= a.m) {
+                if (xin && tb + U_TAIL <= a.m) {
 #pragma unroll
-                    for (int j = 0; j < U_ROWS; ++j, up += a.ld) ulast[j] = __ldg(up);
+                    for (int j = 0; j < U_TAIL; ++j, up += a.ld) ulast[j] = __ldg(up);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < U_ROWS; ++j, up += a.ld) ulast[j] = (xin && tb + j < a.m) ? __ldg(up) : 0.0f;
+                    for (int j = 0; j < U_TAIL; ++j, up += a.ld) ulast[j] = (xin && tb + j < a.m) ? __ldg(up) : 0.0f;
                 }
             };
             load_last(0);
@@ -445,52 +487,77 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 uint32_t u[QT];  // Rec of this thread's 32 snapshots, then r = Rec - U in place
                 tmem_ld16(tmem + lane_addr + TMEM_REC + h * QT, u);
                 tmem_ld16(tmem + lane_addr + TMEM_REC + h * QT + 16, u + 16);
-                const bool interior = xin && (t0 + QT <= a.m);  // no masking needed (all but the ragged last tile / slab)
+                mbar_wait(bar(U_FULL0 + h * U_STAGES), it & 1, 11, it);
+                tmem_ld_wait();
+                // masked == false for every interior (tile, slab): no per-element selects in the common path
+                auto residual = [&](auto masked) {
 #pragma unroll
-                for (int k = 0; k < U_STAGES; ++k) {
-                    const int st = h * U_STAGES + k;
-                    mbar_wait(bar(U_FULL0 + st), it & 1, 11, it);
-                    const uint32_t us = sbase + U_OFF + st * U_STAGE + p * 4;
-                    if (k == 0) tmem_ld_wait();
+                    for (int k = 0; k < U_STAGES; ++k) {
+                        const int st = h * U_STAGES + k;
+                        if (k > 0) mbar_wait(bar(U_FULL0 + st), it & 1, 11, it);
+                        const uint32_t us = sbase + U_OFF + st * U_STAGE + p * 4;
 #pragma unroll
-                    for (int j = 0; j < U_ROWS; ++j) {
-                        float uv;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(uv) : "r"(us + j * (BP * 4)));
-                        float rr = __uint_as_float(u[k * U_ROWS + j]) - uv;
-                        if (!interior) rr = (xin && t0 + k * U_ROWS + j < a.m) ? rr : 0.0f;
-                        u[k * U_ROWS + j] = __float_as_uint(rr);
+                        for (int j = 0; j < U_ROWS; ++j) {
+                            float uv;
+#ifdef EXP_NO_ULDS
+                            uv = __uint_as_float(us);
+#else
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(uv) : "r"(us + j * (BP * 4)));
+#endif
+                            float rr = __uint_as_float(u[k * U_ROWS + j]) - uv;
+                            if (decltype(masked)::value) rr = (xin && t0 + k * U_ROWS + j < a.m) ? rr : 0.0f;
+                            u[k * U_ROWS + j] = __float_as_uint(rr);
+                            lsum = fmaf(rr, rr, lsum);
+                        }
+                        mbar_arrive(bar(U_EMPTY0 + st));
+                    }
+#pragma unroll
+                    for (int j = 0; j < U_TAIL; ++j) {  // last snapshots of the quarter: prefetched into registers one slab ago
+                        float rr = __uint_as_float(u[U_STAGES * U_ROWS + j]) - ulast[j];
+                        if (decltype(masked)::value) rr = (xin && t0 + U_STAGES * U_ROWS + j < a.m) ? rr : 0.0f;
+                        u[U_STAGES * U_ROWS + j] = __float_as_uint(rr);
                         lsum = fmaf(rr, rr, lsum);
                     }
-                    mbar_arrive(bar(U_EMPTY0 + st));
-                }
-#pragma unroll
-                for (int j = 0; j < U_ROWS; ++j) {  // last 8 snapshots of the quarter: prefetched into registers one slab ago
-                    float rr = __uint_as_float(u[3 * U_ROWS + j]) - ulast[j];
-                    if (!interior) rr = (xin && t0 + 3 * U_ROWS + j < a.m) ? rr : 0.0f;
-                    u[3 * U_ROWS + j] = __float_as_uint(rr);
-                    lsum = fmaf(rr, rr, lsum);
-                }
+                };
+                if (xin && (t0 + QT <= a.m)) residual(std::false_type{}); else residual(std::true_type{});
                 tc_fence_before();
                 mbar_arrive(bar(REC_EMPTY));
-                if (slab + 1 < nslab) load_last(slab + 1);  // a whole phase B + G3/G4 ahead of its use
+                // ---- r -> three bf16 planes, formed in REGISTERS while G3/G4 of the previous slab still read R_s: only the 12 vector
+                //      stores below sit between "R_s free" and "R_s full", i.e. on the tensor pipe's critical path ----
+                uint32_t w1[16], w2[16], w3[16];
+#pragma unroll
+                for (int ee = 0; ee < 16; ++ee)
+                    split3_pair(__uint_as_float(u[2 * ee]), __uint_as_float(u[2 * ee + 1]), w1[ee], w2[ee], w3[ee]);
+                {
+                    // ptxas sinks pure arithmetic below the wait loop to shorten live ranges, which would put the whole split back on
+                    // the critical path: consuming every third-plane word (each depends on its first- and second-plane words) in a
+                    // store that precedes the wait pins the split where it is written.  8 LOP3 + 1 STS per thread and slab.
+                    uint32_t x = 0;
+#pragma unroll
+                    for (int ee = 0; ee < 16; ++ee) x ^= w3[ee];
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(&sink_s[lane])), "r"(x) : "memory");
+                }
                 c0 = now(); te[1] += c0 - c1;
-                if (it > 0) mbar_wait(bar(R_EMPTY), (it - 1) & 1, 12, it);
+                if (it > 0) mbar_wait(bar(R_EMPTYQ0 + q), (it - 1) & 1, 12, it);
                 c1 = now(); te[2] += c1 - c0;
-                // ---- r -> three bf16 planes: row p of box (h >> 1), 16 B chunks (h & 1) * 4 .. +3 (8 snapshots each) ----
+                // row p of box (h >> 1), 16 B chunks (h & 1) * 4 .. +3 (8 snapshots each)
                 const uint32_t rs = sbase + R_OFF + (h >> 1) * (BP * 128) + p * 128;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    uint32_t w1[4], w2[4], w3[4];
-#pragma unroll
-                    for (int ee = 0; ee < 4; ++ee)
-                        split3_pair(__uint_as_float(u[c * 8 + 2 * ee]), __uint_as_float(u[c * 8 + 2 * ee + 1]), w1[ee], w2[ee], w3[ee]);
+#ifdef EXP_NO_RSTS
+                    if (a.m > 0) break;
+#endif
                     const uint32_t off = ((uint32_t)(((h & 1) * 4 + c) ^ (p & 7))) << 4;
-                    st_shared_v4(rs + off, w1[0], w1[1], w1[2], w1[3]);
-                    st_shared_v4(rs + R_PLANE + off, w2[0], w2[1], w2[2], w2[3]);
-                    st_shared_v4(rs + 2 * R_PLANE + off, w3[0], w3[1], w3[2], w3[3]);
+                    st_shared_v4(rs + off, w1[4 * c], w1[4 * c + 1], w1[4 * c + 2], w1[4 * c + 3]);
+                    st_shared_v4(rs + R_PLANE + off, w2[4 * c], w2[4 * c + 1], w2[4 * c + 2], w2[4 * c + 3]);
+                    st_shared_v4(rs + 2 * R_PLANE + off, w3[4 * c], w3[4 * c + 1], w3[4 * c + 2], w3[4 * c + 3]);
                 }
+                c0 = now(); te[4] += c0 - c1;
                 fence_async_smem();
                 mbar_arrive(bar(R_FULL));
+                c1 = now(); te[7] += c1 - c0;
+                if (slab + 1 < nslab) load_last(slab + 1);  // after the fence (which would wait for them), a G3/G4 ahead of their use
+                else if (tl + 1 < my_tiles) eval_library(tile + gridDim.x);
                 te[3] += now() - c1;
             }
             loss_acc += (double)lsum;
