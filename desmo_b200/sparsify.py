@@ -26,15 +26,25 @@ def threshold_sweep(model, snapshot_norm2: float, thresholds=None) -> List[Tuple
     return out
 
 
-def greedy_removal(model, snapshot_norm2: float) -> List[Tuple[int, float]]:
-    """TURB:1166-1245: sort terms by norm, remove the smallest one at a time, re-evaluate the relative error."""
+def removal_order(norms: torch.Tensor, T: int, r: int) -> List[int]:
+    """Packed K indices in the order the reference's sweep removes them: the list is built as the polynomial terms, then
+    (sin_i, cos_i, tanh_i) per mode (TURB:1173-1181), and sorted by norm with a stable sort (TURB:1183)."""
+    vals = norms.tolist()
+    listed = list(range(T)) + [T + b * r + i for i in range(r) for b in range(3)]
+    return sorted(listed, key=lambda k: vals[k])
+
+
+def greedy_removal(model, snapshot_norm2: float) -> List[Tuple[int, float, int]]:
+    """TURB:1166-1245: for step = 0..K zero the gates of the ``step`` smallest-norm terms, evaluate ||X - recon^T|| / ||X||
+    (TURB:1227) and count the non-zero gates left (TURB:1229-1234).  One gradient-free fused pass per step on the resident
+    snapshot instead of a DataLoader round trip + host numpy.  Returns [(step, relative_error, nonzero_terms)], gates restored."""
     e = model.engine
-    norms = e.term_norms()
-    order = torch.argsort(norms)
+    order = removal_order(e.term_norms(), e.T, e.r)
     saved = e.gates.clone()
     out = []
-    for k in order.tolist():
-        e.gates[k] = 0.0
-        out.append((k, float((e.residual_norm2() / snapshot_norm2) ** 0.5)))
+    for step in range(e.K + 1):
+        if step:
+            e.gates[order[step - 1]] = 0.0
+        out.append((step, float((e.residual_norm2() / snapshot_norm2) ** 0.5), int((e.gates != 0).sum().item())))
     e.gates.copy_(saved)
     return out

@@ -502,6 +502,25 @@ def relative_error(p: DesmoParams, pod_modes: np.ndarray, snapshot: np.ndarray, 
     return float(np.linalg.norm(snapshot.astype(np.float64) - recon) / np.linalg.norm(snapshot.astype(np.float64)))
 
 
+def removal_order(norms: np.ndarray, T: int, r: int) -> List[int]:
+    """Order in which the greedy sweep removes terms (packed K indices).  The reference lists the polynomial terms first, then
+    (sin_i, cos_i, tanh_i) for i = 0..r-1 (TURB:1173-1181) and sorts that list by norm with Python's stable sort (TURB:1183)."""
+    listed = list(range(T)) + [T + b * r + i for i in range(r) for b in range(3)]
+    return sorted(listed, key=lambda k: float(norms[k]))
+
+
+def greedy_removal(p: DesmoParams, pod_modes: np.ndarray, snapshot: np.ndarray):
+    """Greedy term-removal sweep (TURB:1166-1245): for step = 0..K zero the gates of the ``step`` smallest-norm terms, evaluate
+    ||X - recon^T|| / ||X|| (TURB:1227) and count the non-zero gates left (TURB:1229-1234).  Returns [(step, error, nonzero)]."""
+    order = removal_order(term_norms(p, pod_modes), p.T, p.r)
+    out = []
+    for step in range(p.K + 1):
+        mask = np.ones(p.K, bool)
+        mask[order[:step]] = False
+        out.append((step, relative_error(p, pod_modes, snapshot, mask), int(np.count_nonzero(np.where(mask, p.gates, 0)))))
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md section 8d) -- shared by tests and bench so both sides see identical data
 # ----------------------------------------------------------------------------------------------

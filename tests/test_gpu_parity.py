@@ -398,3 +398,25 @@ def test_device_preprocess_matches_reference_golden(name, cfg, dtype):
     sig = e.pod_from_snapshot()
     _, _, s_ref, _ = orc.pod_analysis(fx[name + "_X"], 2)
     assert rel(sig.cpu().numpy()[:2], s_ref[:2]) < 1e-4
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_greedy_removal_sweep_matches_oracle(path):
+    """TURB:1166-1245 on the device: same removal order, non-zero counts and relative errors as the oracle's restatement."""
+    from desmo_b200 import DESMO
+    from desmo_b200.sparsify import greedy_removal, removal_order
+
+    _, modes, snap, prm = make_case("channel", 700, 72, 4, 2, omega_init=10.0, perturb_rel=0.3)
+    prm.gates[3] = 0.0  # an already-pruned term: counted out of nonzero_terms from step 0, removed first (norm 0)
+    model = DESMO(prm.n, prm.m, 2, 4, 10.0, pod_modes=modes, device=torch.device("cuda:0"), path=path)
+    load_engine(model.engine, prm, modes, snap)
+    want = orc.greedy_removal(prm, modes, snap)
+    norms_ref = orc.term_norms(prm, modes)
+    assert removal_order(model.engine.term_norms(), prm.T, prm.r) == orc.removal_order(norms_ref, prm.T, prm.r)
+    got = greedy_removal(model, float((snap.astype(np.float64) ** 2).sum()))
+    assert len(got) == prm.K + 1 and [g[0] for g in got] == list(range(prm.K + 1))
+    assert [g[2] for g in got] == [w[2] for w in want] and got[0][2] == prm.K - 1 and got[-1][2] == 0
+    for g, w in zip(got, want):
+        assert abs(g[1] - w[1]) < 1e-4 * max(w[1], 1e-3), (g, w)
+    assert abs(got[-1][1] - 1.0) < 1e-6  # everything removed: recon = 0
+    assert rel(model.engine.gates.cpu().numpy(), prm.gates) == 0.0  # gates restored

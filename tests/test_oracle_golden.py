@@ -168,3 +168,23 @@ def test_preprocess_matches_reference_golden(name):
     X, mean = orc.preprocess(fx[name + "_raw"].astype(np.float64), d_in, d_use, mag, True, scale, stride)
     assert X.shape == fx[name + "_X"].shape
     assert np.array_equal(X, fx[name + "_X"]) and np.array_equal(mean, fx[name + "_mean"])
+
+
+def test_greedy_removal_sweep_properties():
+    """TURB:1166-1245 restated: K+1 steps, stable ascending-norm order in the reference's list order, all-removed error == 1."""
+    from tests.helpers import make_case
+
+    _, modes, snap, prm = make_case("channel", 120, 30, 3, 2, omega_init=10.0, perturb_rel=0.3)
+    prm.gates[[2, 5]] = 0.0  # two zero-norm terms: the stable sort keeps the reference's list order (poly 2 before poly 5)
+    norms = orc.term_norms(prm, modes)
+    order = orc.removal_order(norms, prm.T, prm.r)
+    assert order[:2] == [2, 5] and sorted(order) == list(range(prm.K))
+    assert all(norms[a] <= norms[b] for a, b in zip(order, order[1:]))
+    # ties between a nonlinear triple follow (sin_i, cos_i, tanh_i), not the packed [sin | cos | tanh] layout
+    tied = np.ones(prm.K)
+    assert orc.removal_order(tied, prm.T, prm.r)[prm.T:prm.T + 4] == [prm.T, prm.T + prm.r, prm.T + 2 * prm.r, prm.T + 1]
+    res = orc.greedy_removal(prm, modes, snap)
+    assert [s for s, _, _ in res] == list(range(prm.K + 1))
+    assert res[0][2] == prm.K - 2 and res[2][2] == prm.K - 2 and res[-1][2] == 0
+    assert res[0][1] == res[2][1] and abs(res[-1][1] - 1.0) < 1e-12
+    assert res[0][1] == pytest.approx(orc.relative_error(prm, modes, snap))
