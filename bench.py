@@ -271,6 +271,11 @@ def main():
     if not args.no_e2e:
         try:
             lib = _lib.load()
+            import psutil
+
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+            if 4.0 * n * m * local_world > 0.6 * psutil.virtual_memory().available:  # never drive the box out of memory
+                raise RuntimeError(f"host memory too small for {local_world} pinned batches of {4.0 * n * m / 1e9:.1f} GB")
             host = torch.empty(m, n, dtype=torch.float32, pin_memory=True)
             host.copy_(e.U[:, :n])
             ss = ctypes.c_void_p()
@@ -297,7 +302,7 @@ def main():
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             lib.desmo_session_destroy(ss)
-            e2e = {"value": 1.0 / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(n * m * 4), "d2h_bytes_per_step": 16,
+            e2e = {"value": world / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(n * m * 4), "d2h_bytes_per_step": 16,
                    "steps": e_steps, "call": "desmo_session_step_host (pinned host batch -> device, fused step, losses -> host)"}
             del host
         except Exception as ex:  # keep the device-resident number even if the host leg cannot run (e.g. pinned alloc)
