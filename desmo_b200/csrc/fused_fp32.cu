@@ -249,11 +249,20 @@ __global__ void __launch_bounds__(kTile, 1) fused_fp32_kernel(const FusedArgs a)
 // tensor-core path.  The monomial part is ONE reverse sweep over the library: with L_j = L_parent(j) * Phi_last(j) (exactly the
 // left-to-right products of POOL_DATA, CYL:390-431), adj(L_parent) += adj(L_j) * Phi_last and dPhi_last += adj(L_j) * L_parent --
 // two FMAs per term instead of a product per (term, position).
+template <int R>
 __global__ void __launch_bounds__(kTile) chain_rule_kernel(const FusedArgs a, int slot_base) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* red_s = reinterpret_cast<double*>(smem_raw);
     float* fs = reinterpret_cast<float*>(smem_raw + 8 * kScal * sizeof(double));
-    const int r = a.r, T = a.T, K = a.K;
+    constexpr int r = R;
+    const int T = a.T;
+    // per-thread partial sums over all tiles of this CTA (registers; R is a template parameter so that they stay there):
+    // d omega [3R] and the upper triangle of Phi^T Phi; reduced across the CTA once, after the tile loop
+    float om_acc[3 * R], gr_acc[R * (R + 1) / 2];
+#pragma unroll
+    for (int i = 0; i < 3 * R; ++i) om_acc[i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < R * (R + 1) / 2; ++i) gr_acc[i] = 0.0f;
     float* Phi_s = fs;                         // [kMaxR][kTile]
     float* dPhi_s = Phi_s + kMaxR * kTile;     // [kMaxR][kTile]
     float* L_s = dPhi_s + kMaxR * kTile;       // [T][kTile]   library values
@@ -281,6 +290,7 @@ __global__ void __launch_bounds__(kTile) chain_rule_kernel(const FusedArgs a, in
             dPhi_s[v * kTile + tid] = fmaf(adj, L_s[par * kTile + tid], dPhi_s[v * kTile + tid]);
             if (par > 0) A_s[par * kTile + tid] = fmaf(adj, Phi_s[v * kTile + tid], A_s[par * kTile + tid]);
         }
+#pragma unroll
         for (int i = 0; i < r; ++i) {
             const float ph = Phi_s[i * kTile + tid], pod = (x < a.ld) ? a.P[(long long)i * a.ld + x] : 0.0f;
             const float ws = a.omega[3 * i], wc = a.omega[3 * i + 1], wh = a.omega[3 * i + 2];
@@ -294,25 +304,59 @@ __global__ void __launch_bounds__(kTile) chain_rule_kernel(const FusedArgs a, in
             const float sech2 = 1.0f - th * th;
             const float dphi_i = dPhi_s[i * kTile + tid] + (ds * ws * cs - dc * wc * sn + dh * wh * sech2);
             if (x < a.ld) a.dphi[(long long)i * a.ld + x] = dphi_i * pod;
-            const float o0 = warp_sum(ds * ph * cs), o1 = warp_sum(-dc * ph * sn), o2 = warp_sum(dh * ph * sech2);
-            if (lane == 0) {
-                red_s[warp * kScal + 1 + kMaxR * kMaxR + 3 * i] += (double)o0;
-                red_s[warp * kScal + 1 + kMaxR * kMaxR + 3 * i + 1] += (double)o1;
-                red_s[warp * kScal + 1 + kMaxR * kMaxR + 3 * i + 2] += (double)o2;
-            }
+            om_acc[3 * i] += ds * ph * cs;
+            om_acc[3 * i + 1] -= dc * ph * sn;
+            om_acc[3 * i + 2] += dh * ph * sech2;
         }
+        {
+            int g = 0;
+#pragma unroll
+            for (int i = 0; i < r; ++i)
+#pragma unroll
+                for (int j = i; j < r; ++j, ++g) gr_acc[g] = fmaf(Phi_s[i * kTile + tid], Phi_s[j * kTile + tid], gr_acc[g]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3 * R; ++i) {
+        const float v = warp_sum(om_acc[i]);
+        if (lane == 0) red_s[warp * kScal + 1 + kMaxR * kMaxR + i] += (double)v;
+    }
+    {
+        int g = 0;
+#pragma unroll
         for (int i = 0; i < r; ++i)
-            for (int j = i; j < r; ++j) {
-                const float v = warp_sum(Phi_s[i * kTile + tid] * Phi_s[j * kTile + tid]);
+#pragma unroll
+            for (int j = i; j < r; ++j, ++g) {
+                const float v = warp_sum(gr_acc[g]);
                 if (lane == 0) red_s[warp * kScal + 1 + i * kMaxR + j] += (double)v;
             }
     }
-    (void)K;
     __syncthreads();
     for (int i = tid; i < kScal; i += kTile) {
         double s = 0.0;
         for (int w = 0; w < 8; ++w) s += red_s[w * kScal + i];
         a.Spart[(long long)(slot_base + blockIdx.x) * kScal + i] = s;
+    }
+}
+
+// chain_rule_kernel<R> for R = a.r (1..kMaxR)
+template <int R>
+static cudaError_t chain_rule_go(const FusedArgs& a, int slot_base, int gc, size_t sm, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(chain_rule_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+    chain_rule_kernel<R><<<gc, kTile, sm, st>>>(a, slot_base);
+    return cudaGetLastError();
+}
+static cudaError_t chain_rule_dispatch(const FusedArgs& a, int slot_base, int gc, size_t sm, cudaStream_t st) {
+    switch (a.r) {
+        case 1: return chain_rule_go<1>(a, slot_base, gc, sm, st);
+        case 2: return chain_rule_go<2>(a, slot_base, gc, sm, st);
+        case 3: return chain_rule_go<3>(a, slot_base, gc, sm, st);
+        case 4: return chain_rule_go<4>(a, slot_base, gc, sm, st);
+        case 5: return chain_rule_go<5>(a, slot_base, gc, sm, st);
+        case 6: return chain_rule_go<6>(a, slot_base, gc, sm, st);
+        case 7: return chain_rule_go<7>(a, slot_base, gc, sm, st);
+        default: return chain_rule_go<8>(a, slot_base, gc, sm, st);
     }
 }
 
@@ -361,9 +405,7 @@ int chain_rule_launch(const desmo_shape* s, const MonoTable& mt, int T, int Kp, 
     const long long ntiles = (a.ld + kTile - 1) / kTile;
     const int gc = (int)(ntiles < 592 ? ntiles : 592);
     const size_t sm = 8 * kScal * sizeof(double) + (size_t)(2 * kMaxR + 2 * a.T) * kTile * sizeof(float);
-    DESMO_CUDA(cudaFuncSetAttribute(chain_rule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    chain_rule_kernel<<<gc, kTile, sm, st>>>(a, slot_base);
-    DESMO_CUDA(cudaGetLastError());
+    DESMO_CUDA(chain_rule_dispatch(a, slot_base, gc, sm, st));
     *nslots = gc;
     return DESMO_OK;
 }
@@ -398,9 +440,7 @@ static int launch_fused(const FusedArgs& a, int sms, size_t smem_cap, cudaStream
     if (nchunk > 1) {
         const int gc = (int)(ntiles < 256 ? ntiles : 256);
         const size_t sm = 8 * kScal * sizeof(double) + (size_t)(2 * kMaxR + 2 * a.T) * kTile * sizeof(float);
-        DESMO_CUDA(cudaFuncSetAttribute(chain_rule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        chain_rule_kernel<<<gc, kTile, sm, st>>>(b, nslots);
-        DESMO_CUDA(cudaGetLastError());
+        DESMO_CUDA(chain_rule_dispatch(b, nslots, gc, sm, st));
         nslots += gc;
     }
     *gx_out = gx;
