@@ -361,13 +361,23 @@ static cudaError_t chain_rule_dispatch(const FusedArgs& a, int slot_base, int gc
 }
 
 // Deterministic second stage: sum the per-CTA partials in a fixed order into `red`.
-__global__ void reduce_partials_kernel(const float* __restrict__ Epart, int nx, long long ecount,
-                                       const double* __restrict__ Spart, int nslots, int r, float* __restrict__ red) {
-    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o < ecount) {
-        float s = 0.0f;
-        for (int b = 0; b < nx; ++b) s += Epart[(long long)b * ecount + o];
-        red[o] = s;
+// 32 outputs per CTA, 8 warps: warp w sums the partials b = w, w+8, ... of 32 consecutive outputs (coalesced), the eight sums are
+// added in warp order -- a fixed order, so the result does not depend on scheduling.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ Epart, int nx, long long ecount,
+                                                              const double* __restrict__ Spart, int nslots, int r, float* __restrict__ red) {
+    __shared__ float part_s[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long o = (long long)blockIdx.x * 32 + lane;
+    float s = 0.0f;
+    if (o < ecount)
+        for (int b = w; b < nx; b += 8) s += __ldg(Epart + (long long)b * ecount + o);
+    part_s[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && o < ecount) {
+        float t = part_s[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += part_s[k][lane];
+        red[o] = t;
     }
     if (blockIdx.x == 0 && threadIdx.x < kScal) {
         const int i = threadIdx.x;
@@ -390,7 +400,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ Epart, int nx, 
 }
 
 void reduce_partials_launch(const float* Epart, int nx, long long ecount, const double* Spart, int nslots, int r, float* red, cudaStream_t st) {
-    reduce_partials_kernel<<<(unsigned)((ecount + 255) / 256), 256, 0, st>>>(Epart, nx, ecount, Spart, nslots, r, red);
+    reduce_partials_kernel<<<(unsigned)((ecount + 31) / 32), 256, 0, st>>>(Epart, nx, ecount, Spart, nslots, r, red);
 }
 
 // Chain rule for a D matrix left in ws.Dacc by the tensor-core kernel (same kernel the chunked FFMA path uses).
@@ -470,7 +480,7 @@ int fused_fp32(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const f
     }
     if (rc) return rc;
     const long long ecount = (long long)Kp * s->mld;
-    reduce_partials_kernel<<<(unsigned)((ecount + 255) / 256), 256, 0, st>>>(ws.Epart, gx, ecount, ws.Spart, nslots, s->r, red);
+    reduce_partials_kernel<<<(unsigned)((ecount + 31) / 32), 256, 0, st>>>(ws.Epart, gx, ecount, ws.Spart, nslots, s->r, red);
     DESMO_CUDA(cudaGetLastError());
     return DESMO_OK;
 }
