@@ -29,6 +29,7 @@ WORKLOADS = {
     "aneurysm-scale": (3 * 2 ** 20, 1000, 4, 2, 0),
     "aneurysm-script": (27000, 1000, 4, 2, 0),
     "cylinder-script": (3961, 1001, 4, 3, 0),
+    "cylinder-8modes": (3961, 1001, 8, 2, 0),   # BASELINE.json configs[0] ("8 modes"): K = 69, FFMA path
     "cylinder-fourier": (3961, 1001, 2, 2, 10),
     "channel-script": (16384, 1000, 4, 2, 0),
 }

@@ -12,7 +12,7 @@ HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "desmo_b200.h")
 
 PATH_AUTO, PATH_FP32, PATH_TC = 0, 1, 2
 HYP_LR_GATES, HYP_LR_PHI, HYP_LR_Z, HYP_LR_OMEGA, HYP_LR_PERIOD, HYP_BETA, HYP_L1_LAMBDA, HYP_COUNT = range(8)
-MAX_R, MAX_P, MAX_K = 8, 7, 64
+MAX_R, MAX_P, MAX_K = 8, 7, 80
 PRE_MAGNITUDE, PRE_SUBTRACT_MEAN, PRE_SCALE_SQRT_M = 1, 2, 4
 
 

@@ -476,6 +476,7 @@ int fused_fp32(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const f
         case 32: rc = launch_fused<32>(a, sms, smem_cap, st, &gx, &nslots); break;
         case 48: rc = launch_fused<48>(a, sms, smem_cap, st, &gx, &nslots); break;
         case 64: rc = launch_fused<64>(a, sms, smem_cap, st, &gx, &nslots); break;
+        case 80: rc = launch_fused<80>(a, sms, smem_cap, st, &gx, &nslots); break;  // r = 8, p = 2 (K = 69): BASELINE's "8 modes"
         default: set_error("fused_fp32: padded K=%d not instantiated", Kp); return DESMO_ERR_UNSUPPORTED;
     }
     if (rc) return rc;

@@ -43,7 +43,7 @@ extern "C" {
 
 #define DESMO_MAX_R 8
 #define DESMO_MAX_P 7
-#define DESMO_MAX_K 64
+#define DESMO_MAX_K 80
 
 #define DESMO_PATH_AUTO 0
 #define DESMO_PATH_FP32 1  /* FFMA path */

@@ -24,6 +24,7 @@ def test_library_term_counts_match_reference_facts():
     for (r, p) in [(4, 3), (4, 2), (2, 2), (3, 4), (2, 7), (8, 1)]:
         assert lib.desmo_num_terms(r, p) == orc.number_of_terms(r, p)
         assert lib.desmo_padded_k(r, p) % 16 == 0 and lib.desmo_padded_k(r, p) >= orc.number_of_terms(r, p) + 3 * r
+    assert lib.desmo_num_terms(8, 2) == 45 and lib.desmo_padded_k(8, 2) == 80  # BASELINE's "8 modes": K = 69
     assert lib.desmo_num_terms(8, 3) < 0  # K = 189 > DESMO_MAX_K: reported as unsupported, never silently truncated
     assert lib.desmo_num_terms(2, 8) < 0 and lib.desmo_num_terms(0, 2) < 0
 

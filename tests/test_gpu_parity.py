@@ -75,6 +75,8 @@ CASES = [  # (kind, n, m, r, p, nF) -- ragged sizes, single tile, multi tile, ch
     ("aneurysm", 37, 17, 2, 1, None),       # smaller than one tile / one slab
     ("cylinder", 513, 33, 8, 1, None),      # r = 8 (K = 33 -> Kp = 48)
     ("cylinder", 300, 40, 3, 3, 3),         # Fourier, odd sizes
+    ("cylinder", 3961, 1001, 8, 2, None),   # C1 with BASELINE's "8 modes": K = 69 -> Kp = 80 (FFMA path)
+    ("cylinder", 700, 90, 8, 2, 4),         # 8 modes, Fourier temporal library
 ]
 
 
