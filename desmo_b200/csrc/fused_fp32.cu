@@ -8,6 +8,8 @@
 //   B3  E[k][t] += sum_x G[x][k] r[x][t]          cross-thread: R slab + G tile staged in smem, E chunk resident in smem
 // After the last slab the chain rule through POOL_DATA / sin / cos / tanh / (phi * POD) is applied in place (single
 // chunk) or d is accumulated to Dacc for the chain-rule kernel (chunked time axis, large K*m).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace desmo {
@@ -434,10 +436,18 @@ static int launch_fused(const FusedArgs& a, int sms, size_t smem_cap, cudaStream
         }
     }
     nchunk = (a.mld + mc - 1) / mc;
+    const long long ntiles = (a.ld + kTile - 1) / kTile;
+    // small meshes (the script-sized cylinder cases are 16 tiles): split the time axis further so that every SM gets a CTA
+    if (ntiles * nchunk < sms) {
+        const int want = (int)std::min<long long>(sms / ntiles, a.mld / (4 * kBT));
+        if (want > nchunk) {
+            mc = (((a.mld + want - 1) / want) + kBT - 1) / kBT * kBT;
+            nchunk = (a.mld + mc - 1) / mc;
+        }
+    }
     FusedArgs b = a;
     b.nchunk = nchunk;
     b.mc = mc;
-    const long long ntiles = (a.ld + kTile - 1) / kTile;
     const int per_chunk = sms / nchunk > 0 ? sms / nchunk : 1;
     const int gx = (int)(ntiles < per_chunk ? ntiles : per_chunk);
     DESMO_CUDA(cudaFuncSetAttribute(fused_fp32_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes(mc)));
