@@ -57,6 +57,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
                    "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr) : "memory");
 }
+// volatile: keeps the next chunk's loads BELOW the current chunk's split + stores (hoisted, they double the live registers and spill)
+__device__ __forceinline__ float4 ldg_nc_v4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -129,34 +135,42 @@ __global__ void __launch_bounds__(THREADS, 1) gram_tc_kernel(const float* __rest
             }
         }
     } else if (warp >= 4) {
-        // ---------------- converters: thread <-> (row of the tile, half of the 64-point chunk) ----------------
+        // ---------------- converters: 1024 (row, 8-point group) items per operand and chunk, 4 per thread; lanes 0-7 of a warp
+        //                  cover the 256 contiguous bytes of one row, so every warp-level load is four full 256 B segments ----------------
         const int ct = tid - 128;            // 0..255
-        const int row = ct >> 1, half = ct & 1;
-        const int ta = bi * BM + row, tb = bj * BM + row;
-        const float* pa = U + (long long)ta * ld + x0 + half * 32;
-        const float* pb = U + (long long)tb * ld + x0 + half * 32;
-        const bool va = ta < m, vb = (!diag) && tb < m;
         float4 ra[8], rb[8];
         auto load_chunk = [&](int c) {
-            const long long xo = (long long)c * BK;
+            const long long xo = x0 + (long long)c * BK;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const bool inx = x0 + xo + half * 32 + i * 4 < x1;
-                ra[i] = (va && inx) ? __ldg(reinterpret_cast<const float4*>(pa + xo) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (!diag) rb[i] = (vb && inx) ? __ldg(reinterpret_cast<const float4*>(pb + xo) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < 4; ++k) {
+                const int idx = k * 256 + ct, row = idx >> 3, g8 = idx & 7;
+                const long long x = xo + g8 * 8;
+                const int ta = bi * BM + row, tb = bj * BM + row;
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4* qa = reinterpret_cast<const float4*>(U + (long long)ta * ld + x);
+                const bool va = ta < m && x < x1;
+                ra[2 * k] = va ? ldg_nc_v4(qa) : z;
+                ra[2 * k + 1] = va ? ldg_nc_v4(qa + 1) : z;
+                if (!diag) {
+                    const float4* qb = reinterpret_cast<const float4*>(U + (long long)tb * ld + x);
+                    const bool vb = tb < m && x < x1;
+                    rb[2 * k] = vb ? ldg_nc_v4(qb) : z;
+                    rb[2 * k + 1] = vb ? ldg_nc_v4(qb + 1) : z;
+                }
             }
         };
-        auto store_planes = [&](uint32_t base, const float4* r) {
-            // row `row` of the operand, 16 B chunks half*4 .. half*4+3 (8 points each), 128B swizzle
+        auto store_planes = [&](uint32_t base, const float4 (&r)[8]) {
+            // row `row` of the operand, 16 B chunk g8 (8 points), 128B swizzle; a warp writes four whole 128 B rows per plane
 #pragma unroll
-            for (int cidx = 0; cidx < 4; ++cidx) {
+            for (int k = 0; k < 4; ++k) {
+                const int idx = k * 256 + ct, row = idx >> 3, g8 = idx & 7;
                 uint32_t w1[4], w2[4], w3[4];
-                const float4 lo = r[2 * cidx], hi = r[2 * cidx + 1];
+                const float4 lo = r[2 * k], hi = r[2 * k + 1];
                 split3_pair(lo.x, lo.y, w1[0], w2[0], w3[0]);
                 split3_pair(lo.z, lo.w, w1[1], w2[1], w3[1]);
                 split3_pair(hi.x, hi.y, w1[2], w2[2], w3[2]);
                 split3_pair(hi.z, hi.w, w1[3], w2[3], w3[3]);
-                const uint32_t off = row * 128 + ((uint32_t)((half * 4 + cidx) ^ (row & 7)) << 4);
+                const uint32_t off = row * 128 + ((uint32_t)(g8 ^ (row & 7)) << 4);
                 st_shared_v4(base + off, w1[0], w1[1], w1[2], w1[3]);
                 st_shared_v4(base + PLANE + off, w2[0], w2[1], w2[2], w2[3]);
                 st_shared_v4(base + 2 * PLANE + off, w3[0], w3[1], w3[2], w3[3]);
@@ -183,17 +197,20 @@ __global__ void __launch_bounds__(THREADS, 1) gram_tc_kernel(const float* __rest
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
                     uint32_t v[16];
+                    float old[16];
+                    float* const pp = mypart + (hcol * 64 + cc * 16) * BM + q * 32 + lane;
+                    // the 16 partial sums first (independent L2 loads in flight together; one by one they cost a full L2 round trip each)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) old[j] = (f == 0) ? 0.0f : __ldcg(pp + j * BM);
                     tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + hcol * 64 + cc * 16, v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int col = hcol * 64 + cc * 16 + j;
-                        float* pp = mypart + col * BM + q * 32 + lane;
-                        const float val = (f == 0 ? 0.0f : *pp) + __uint_as_float(v[j]);
+                        const float val = old[j] + __uint_as_float(v[j]);
                         if (!last) {
-                            *pp = val;
+                            __stcg(pp + j * BM, val);
                         } else {
-                            const int tcol = bj * BM + col;
+                            const int tcol = bj * BM + hcol * 64 + cc * 16 + j;
                             if (trow < m && tcol < m) {
                                 atomicAdd(C + (long long)trow * m + tcol, val);
                                 if (!diag) atomicAdd(C + (long long)tcol * m + trow, val);
