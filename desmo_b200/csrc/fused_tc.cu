@@ -388,15 +388,19 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         uint32_t v[16];
+                        float old[16];
+                        float* const dst = Eo + (long long)(c * 16) * a.mld + t;
+                        const bool mine = t < a.mld;
+                        // all 16 partial sums first: independent L2 loads in flight together (one by one each costs a round trip)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            old[j] = (mine && !first && c * 16 + j < a.kp_out) ? __ldcg(dst + (long long)j * a.mld) : 0.0f;
                         tmem_ld16(tmem + lane_addr + TMEM_E + slab * KP + c * 16, v);
                         tmem_ld_wait();
-                        if (t < a.mld) {
+                        if (mine) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
-                                if (c * 16 + j < a.kp_out) {
-                                    float* dst = Eo + (long long)(c * 16 + j) * a.mld + t;
-                                    *dst = first ? __uint_as_float(v[j]) : *dst + __uint_as_float(v[j]);
-                                }
+                                if (c * 16 + j < a.kp_out) __stcg(dst + (long long)j * a.mld, old[j] + __uint_as_float(v[j]));
                         }
                     }
                 }
