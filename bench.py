@@ -47,25 +47,48 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons DURING the timed region: NVML polled every 2 ms (nvidia-smi as a fallback, ~10 Hz)."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, index: int):
-        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.index, self.samples, self._stop = index, [], threading.Event()  # samples: (sm_mhz, sm_max_mhz, {reasons})
         self.th = threading.Thread(target=self._run, daemon=True)
+        self.source = "nvml"
 
-    def _run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            mask = int(get_reasons(h))
+            self.samples.append((int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(mx), {n for n, b in self.BITS if mask & b}))
+            self._stop.wait(0.002)
+
+    def _run_smi(self):
+        self.source = "nvidia-smi"
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([c.strip() for c in out.split(",")])
+                c = [v.strip() for v in out.split(",")]
+                if len(c) >= 6 and c[0].isdigit():
+                    names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+                    self.samples.append((int(c[0]), int(c[1]), {n for n, v in zip(names, c[2:6]) if v.lower().startswith("active")}))
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.05)
+
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
 
     def __enter__(self):
         self.th.start()
@@ -76,15 +99,11 @@ class ClockSampler:
         self.th.join(timeout=6)
 
     def summary(self):
-        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
-        reasons = set()
-        for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = set().union(*[s[2] for s in self.samples]) if self.samples else set()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": max(s[1] for s in self.samples) if self.samples else None, "reasons": sorted(reasons),
+                "samples": len(self.samples), "source": self.source}
 
 
 def synth_on_device(torch, n, m, dev, seed, x_offset=0, n_global=None):
