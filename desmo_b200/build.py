@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         fh.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB, *objs, "-lcudart"]
     subprocess.run(cmd, check=True)
     with open(stamp, "w") as fh:
         fh.write(dg)

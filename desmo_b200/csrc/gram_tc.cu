@@ -177,7 +177,6 @@ __global__ void __launch_bounds__(THREADS, 1) gram_tc_kernel(const float* __rest
             }
         };
         const int q = warp & 3, hcol = (warp - 4) >> 2;
-        const int trow = bi * BM + q * 32 + lane;
         float* mypart = part + (long long)(blockIdx.y * gridDim.x + blockIdx.x) * (BM * BM);  // [col][row]: lanes -> consecutive rows
         if (nchunks > 0) load_chunk(0);
         for (int c = 0; c < nchunks; ++c) {
@@ -191,7 +190,6 @@ __global__ void __launch_bounds__(THREADS, 1) gram_tc_kernel(const float* __rest
             if ((c + 1) % FLUSH == 0 || c == nchunks - 1) {
                 // ---- drain the accumulator tile: partial += TMEM (fp32 RN); the last drain goes to C (and its mirror) ----
                 const int f = c / FLUSH;
-                const bool last = (c == nchunks - 1);
                 mbar_wait(bar(ACC_FULL), f & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -206,16 +204,7 @@ __global__ void __launch_bounds__(THREADS, 1) gram_tc_kernel(const float* __rest
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float val = old[j] + __uint_as_float(v[j]);
-                        if (!last) {
-                            __stcg(pp + j * BM, val);
-                        } else {
-                            const int tcol = bj * BM + hcol * 64 + cc * 16 + j;
-                            if (trow < m && tcol < m) {
-                                atomicAdd(C + (long long)trow * m + tcol, val);
-                                if (!diag) atomicAdd(C + (long long)tcol * m + trow, val);
-                            }
-                        }
+                        __stcg(pp + j * BM, old[j] + __uint_as_float(v[j]));  // the per-CTA partial tile; summed in a fixed order below
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -228,6 +217,25 @@ __global__ void __launch_bounds__(THREADS, 1) gram_tc_kernel(const float* __rest
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+    }
+}
+
+// C (and its mirror) = sum over the point ranges of the per-CTA partial tiles, in a fixed order: the Gram matrix, and with it the POD
+// modes, are bit-reproducible from run to run (atomics into C were not).
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restrict__ part, int npairs, int nsplit, int m, int ntile,
+                                                          float* __restrict__ C) {
+    int pair = blockIdx.x, bi = 0;
+    while (pair >= ntile - bi) { pair -= ntile - bi; ++bi; }
+    const int bj = bi + pair;
+    for (int e = threadIdx.x; e < BM * BM; e += 256) {
+        const int col = e / BM, row = e % BM;  // partial tiles are [col][row]
+        float s = 0.0f;
+        for (int y = 0; y < nsplit; ++y) s += __ldg(part + ((long long)y * npairs + blockIdx.x) * (BM * BM) + e);
+        const int trow = bi * BM + row, tcol = bj * BM + col;
+        if (trow < m && tcol < m) {
+            C[(long long)trow * m + tcol] = s;
+            if (bi != bj) C[(long long)tcol * m + trow] = s;
+        }
     }
 }
 
@@ -253,6 +261,8 @@ int pod_gram_tc(const desmo_shape* s, const float* U, float* C, void* workspace,
     DESMO_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     if ((long long)npairs * nsplit > sms) return DESMO_ERR_UNSUPPORTED;  // one partial tile per SM in the workspace
     gram_tc_kernel<<<dim3(npairs, (unsigned)nsplit), THREADS, SMEM_BYTES, st>>>(U, s->ld, m, ntile, xchunk, xtotal, C, part);
+    DESMO_CUDA(cudaGetLastError());
+    gram_reduce_kernel<<<npairs, 256, 0, st>>>(part, npairs, (int)nsplit, m, ntile, C);
     DESMO_CUDA(cudaGetLastError());
     return DESMO_OK;
 }
