@@ -4,13 +4,18 @@
 //
 // One persistent CTA per SM; a CTA owns tiles of 128 mesh points and walks all snapshots in slabs of 128:
 //   G1  Rec[p x t]    = G[p x lib] W[lib x t]           -> TMEM cols [0,128)                      (CYL:548,565-572)
-//   epi r = Rec - U   (U read once from HBM, coalesced, straight into registers; R never leaves the SM) (CYL:722)
-//       r -> three bf16 planes in smem  R_s[p rows][t contiguous]  (128B-swizzled, K-major for G3 AND MN-major for G4)
-//   G3  D[p x lib]   += R[p x t] W^T[t x lib]           -> TMEM cols [128,160), accumulated over the slabs of a tile
-//   G4  E^T[t x lib] += R^T[t x p] G[p x lib]           -> TMEM cols [256+32*slab, +32), accumulated over ALL tiles of the CTA
-// Warp roles: warp 0 = TMA producer (W slab planes), warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..11 = epilogue
-// (thread <-> mesh point == TMEM lane; warps 4-7 take snapshots 0-63 of the slab, warps 8-11 snapshots 64-127).
-// The MMA issuer runs G1 of slab s+1 ahead of G3/G4 of slab s, so the tensor pipe works while the epilogue forms R.
+//   epi r = Rec - U   (U read once from HBM: 24 of a quarter's 32 snapshots through a private TMA ring, 8 by prefetching loads;
+//       R never leaves the SM) (CYL:722); sum r^2;
+//       r -> three bf16 planes (formed in registers before R_s is free), then R_s[p rows][t contiguous] in shared memory
+//       (128B-swizzled: K-major operand of G3 AND MN-major operand of G4)
+//   G3  D[p x lib]   += R[p x t] W^T[t x lib]           -> TMEM cols [128,224): three N-stacked blocks, accumulated over the slabs
+//   G4  E^T[t x lib] += R^T[t x p] G[p x lib]           -> TMEM cols [256+32*slab, +32), accumulated over the tiles of the CTA and
+//       drained every 32 tiles into the CTA's fp32 partial (the tensor core truncates when it adds into the accumulator)
+// Warp roles (20 warps): warp 0 = TMA producer (W slab planes), warp 1 = MMA issuer (one elected thread), warps 2-3 = TMA
+// producers of U (warp 2 also allocates TMEM), warps 4..19 = epilogue: thread <-> (mesh point == TMEM lane, snapshot quarter h);
+// warp e = 4 + 4h + q handles lane quadrant q and snapshots 32h..32h+31 of the slab.
+// The MMA issuer runs G1 of slab s+1 ahead of G3/G4 of slab s, so the tensor pipe works while the epilogue forms R; G4 releases
+// R_s lane quadrant by lane quadrant; the library row of the next tile is evaluated under the last slab's MMAs.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
