@@ -141,8 +141,12 @@ int desmo_session_set_hyper(desmo_session* ss, const float* lrs /*[5]*/, float b
 int desmo_session_upload_snapshot_host(desmo_session* ss, const float* snapshot_host) {
     if (!ss || !snapshot_host) { set_error("desmo_session_upload_snapshot_host: null"); return DESMO_ERR_ARG; }
     const desmo_shape& s = ss->s;
-    DESMO_CUDA(cudaMemcpy2DAsync(ss->U, s.ld * sizeof(float), snapshot_host, s.n * sizeof(float), s.n * sizeof(float), s.m,
-                                 cudaMemcpyHostToDevice, ss->st));
+    if (s.n == s.ld) {  // no padding between snapshots: one contiguous transfer
+        DESMO_CUDA(cudaMemcpyAsync(ss->U, snapshot_host, sizeof(float) * (size_t)s.n * s.m, cudaMemcpyHostToDevice, ss->st));
+    } else {
+        DESMO_CUDA(cudaMemcpy2DAsync(ss->U, s.ld * sizeof(float), snapshot_host, s.n * sizeof(float), s.n * sizeof(float), s.m,
+                                     cudaMemcpyHostToDevice, ss->st));
+    }
     return DESMO_OK;
 }
 
