@@ -341,6 +341,44 @@ def test_tensor_core_path_matches_ffma_path_at_scale():
     assert abs(bias) < 5e-6, bias
 
 
+def test_tensor_core_training_matches_ffma_training_at_scale():
+    """40 fused train steps (CUDA-graph replay, device Adamax) at 2^19 points x 1000 snapshots on the tcgen05 path and on the
+    independent FFMA path from the same state: the parameter trajectories stay within the north_star's 1e-3, and two runs of the
+    tensor-core path are bit-identical (fixed-order partial sums everywhere)."""
+    from desmo_b200 import DesmoEngine, DesmoTrainer
+
+    n, m = 1 << 19, 1000
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.linspace(0, 1, n, device=dev)
+    t = torch.linspace(0, 1, m, device=dev)
+    U = sum(torch.cos(6.2832 * (k + 1) * t + k)[:, None] * torch.sin(3.1416 * (k + 1) * x + 0.3 * k)[None, :] / (k + 1) for k in range(5))
+    U = (U + 0.02 * torch.randn(m, n, device=dev, generator=g)).float()
+    U -= U.mean(dim=0, keepdim=True)
+    P = torch.stack([torch.sin(3.1416 * (k + 1) * x + 0.3 * k) for k in range(4)]) * (2.0 / n) ** 0.5
+    res = []
+    for path in (1, 2, 2):
+        e = DesmoEngine(n, m, 2, 4, omega_init=10.0, device=dev, path=path)
+        e.P[:, :n] = P
+        e.phi[:, :n] = 1.0
+        e.rows[:, :m] = 1.0
+        e.set_snapshot(U)
+        tr = DesmoTrainer(e, lrs=(1e-2, 1e-3, 1e-2, 1e-2), beta=1e-3, l1_lambda=1e-4)
+        first = tr.step()  # epoch 0 is a scheduler epoch: (mse, ortho, l1, total) before the first update
+        for _ in range(39):
+            tr.step()
+        torch.cuda.synchronize()
+        res.append({k: getattr(e, k).detach().double().cpu().numpy() for k in ("phi", "gates", "rows", "omega")}
+                   | {"loss": e.losses.cpu().numpy(), "first": first[0]})
+        del tr, e
+    ffma, tc_a, tc_b = res
+    for k in ("phi", "gates", "rows", "omega"):
+        assert rel(tc_a[k], ffma[k]) < 1e-3, (k, rel(tc_a[k], ffma[k]))
+        assert np.array_equal(tc_a[k], tc_b[k]), k
+    assert abs(tc_a["loss"][0] - ffma["loss"][0]) < 1e-4 * ffma["loss"][0]
+    assert tc_a["loss"][0] < tc_a["first"]  # it actually trains
+
+
 def test_checkpoint_resume_is_exact(tmp_path):
     """Trainer checkpoint (weights in the reference key layout + Adamax moments, step, scheduler, POD modes): 40 steps straight ==
     20 steps, save, fresh objects, load, 20 steps -- bit for bit."""
