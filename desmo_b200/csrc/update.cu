@@ -141,24 +141,56 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
         const float beta = a.hyper[DESMO_HYP_BETA];
         const float clr = clr_of(a.hyper[DESMO_HYP_LR_PHI], step);
         const long long nb = gridDim.x - a.K - 1;
-        for (long long x = (long long)(b - a.K - 1) * 256 + tid; x < a.n; x += nb * 256) {
-            float lat[kMaxR], pod[kMaxR];
+        // four consecutive points per thread (128-bit accesses; ld is a multiple of 256 floats, so every row stays 16 B aligned);
+        // the arithmetic per element is unchanged
+        for (long long x = ((long long)(b - a.K - 1) * 256 + tid) * 4; x < a.n; x += nb * 256 * 4) {
+            const int cnt = (a.n - x >= 4) ? 4 : (int)(a.n - x);
+            float lat[kMaxR][4], pod[kMaxR][4];
 #pragma unroll
             for (int i = 0; i < kMaxR; ++i) {
-                pod[i] = (i < r) ? a.P[(long long)i * a.ld + x] : 0.0f;
-                lat[i] = (i < r) ? a.phi[(long long)i * a.ld + x] * pod[i] : 0.0f;
+                if (i < r) {
+                    const float4 pv = *reinterpret_cast<const float4*>(a.P + (long long)i * a.ld + x);  // pad columns exist up to ld
+                    const float4 fv = *reinterpret_cast<const float4*>(a.phi + (long long)i * a.ld + x);
+                    pod[i][0] = pv.x; pod[i][1] = pv.y; pod[i][2] = pv.z; pod[i][3] = pv.w;
+                    lat[i][0] = fv.x * pv.x; lat[i][1] = fv.y * pv.y; lat[i][2] = fv.z * pv.z; lat[i][3] = fv.w * pv.w;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) pod[i][c] = lat[i][c] = 0.0f;
+                }
             }
 #pragma unroll
             for (int i = 0; i < kMaxR; ++i) {
                 if (i < r) {
-                    float o = 0.0f;
+                    const long long off = (long long)i * a.ld + x;
+                    const float4 dv = *reinterpret_cast<const float4*>(a.dphi + off);
+                    const float dd[4] = {dv.x, dv.y, dv.z, dv.w};
+                    float g[4];
 #pragma unroll
-                    for (int j = 0; j < kMaxR; ++j)
-                        if (j < r) o = fmaf(gsign[i * r + j], lat[j], o);
-                    const float g = a.dphi[(long long)i * a.ld + x] + beta * o * pod[i];
-                    if (a.apply) adamax(a.phi + (long long)i * a.ld + x, a.phi_m + (long long)i * a.ld + x,
-                                        a.phi_u + (long long)i * a.ld + x, g, clr);
-                    else a.dphi_out[(long long)i * a.ld + x] = g;
+                    for (int c = 0; c < 4; ++c) {
+                        float o = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < kMaxR; ++j)
+                            if (j < r) o = fmaf(gsign[i * r + j], lat[j][c], o);
+                        g[c] = dd[c] + beta * o * pod[i][c];
+                    }
+                    if (a.apply) {
+                        float4 pv = *reinterpret_cast<float4*>(a.phi + off), mv = *reinterpret_cast<float4*>(a.phi_m + off),
+                               uv = *reinterpret_cast<float4*>(a.phi_u + off);
+                        float pp[4] = {pv.x, pv.y, pv.z, pv.w}, mm[4] = {mv.x, mv.y, mv.z, mv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (c < cnt) adamax(&pp[c], &mm[c], &uu[c], g[c], clr);
+                        *reinterpret_cast<float4*>(a.phi + off) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+                        *reinterpret_cast<float4*>(a.phi_m + off) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+                        *reinterpret_cast<float4*>(a.phi_u + off) = make_float4(uu[0], uu[1], uu[2], uu[3]);
+                    } else {
+                        float4 ov = *reinterpret_cast<float4*>(a.dphi_out + off);
+                        float oo[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (c < cnt) oo[c] = g[c];
+                        *reinterpret_cast<float4*>(a.dphi_out + off) = make_float4(oo[0], oo[1], oo[2], oo[3]);
+                    }
                 }
             }
         }
@@ -166,7 +198,7 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
 }
 
 int launch_update(const UpdateArgs& a, cudaStream_t st) {
-    long long nb = (a.n + 255) / 256;
+    long long nb = (a.n + 1023) / 1024;  // 4 points per thread in the phi role
     if (nb > 148 * 8) nb = 148 * 8;
     if (nb < 1) nb = 1;
     if (a.nF > 64) { set_error("update: nF > 64 not supported"); return DESMO_ERR_UNSUPPORTED; }
