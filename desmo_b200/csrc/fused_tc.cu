@@ -410,12 +410,14 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                     }
                 }
             }
-            tc_fence_before();
-            mbar_arrive(bar(D_EMPTY));
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 if (h * 8 + j < a.kp_out)
                     a.Dacc[(long long)(h * 8 + j) * a.ld + x] = (__uint_as_float(v2[j]) + __uint_as_float(v1[j])) + __uint_as_float(v0[j]);
+            // the accumulator is handed back only after the loaded registers were consumed: an experiment that arrived on REC_EMPTY
+            // straight after tcgen05.wait::ld (before using the data) produced wrong residuals in a few columns (profiles/README.md)
+            tc_fence_before();
+            mbar_arrive(bar(D_EMPTY));
         };
 
         // ---- library row of a point (CYL:538-548,565-567).  The four quarters share the work (quarter h takes library terms
@@ -498,6 +500,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 tmem_ld16(tmem + lane_addr + TMEM_REC + h * QT + 16, u + 16);
                 mbar_wait(bar(U_FULL0 + h * U_STAGES), it & 1, 11, it);
                 tmem_ld_wait();
+#ifdef EXP_EARLY_REC
+                tc_fence_before();
+                mbar_arrive(bar(REC_EMPTY));
+#endif
                 // masked == false for every interior (tile, slab): no per-element selects in the common path
                 auto residual = [&](auto masked) {
 #pragma unroll
@@ -529,8 +535,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                     }
                 };
                 if (xin && (t0 + QT <= a.m)) residual(std::false_type{}); else residual(std::true_type{});
+#ifndef EXP_EARLY_REC
                 tc_fence_before();
                 mbar_arrive(bar(REC_EMPTY));
+#endif
                 // ---- r -> three bf16 planes, formed in REGISTERS while G3/G4 of the previous slab still read R_s: only the 12 vector
                 //      stores below sit between "R_s free" and "R_s full", i.e. on the tensor pipe's critical path ----
                 uint32_t w1[16], w2[16], w3[16];
