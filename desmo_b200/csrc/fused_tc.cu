@@ -501,6 +501,14 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 mbar_wait(bar(U_FULL0 + h * U_STAGES), it & 1, 11, it);
                 tmem_ld_wait();
 #ifdef EXP_EARLY_REC
+#ifdef EXP_EARLY_REC_DEP
+                {
+                    uint32_t xx = 0;
+#pragma unroll
+                    for (int j = 0; j < QT; ++j) xx ^= u[j];
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(&sink_s[lane])), "r"(xx) : "memory");
+                }
+#endif
                 tc_fence_before();
                 mbar_arrive(bar(REC_EMPTY));
 #endif
@@ -523,6 +531,16 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                             if (decltype(masked)::value) rr = (xin && t0 + k * U_ROWS + j < a.m) ? rr : 0.0f;
                             u[k * U_ROWS + j] = __float_as_uint(rr);
                             lsum = fmaf(rr, rr, lsum);
+                        }
+                        {
+                            // The stage may only be released once the eight ld.shared above have RETURNED: an mbarrier arrive is not
+                            // held back by loads still in flight, and the refilling TMA was observed to overwrite rows 5-7 of a stage
+                            // under shared-memory congestion (profiles/README.md).  A store that consumes all eight residuals
+                            // precedes the arrive in the same in-order pipeline.
+                            uint32_t xx = 0;
+#pragma unroll
+                            for (int j = 0; j < U_ROWS; ++j) xx ^= u[k * U_ROWS + j];
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(&sink_s[lane])), "r"(xx) : "memory");
                         }
                         mbar_arrive(bar(U_EMPTY0 + st));
                     }
