@@ -38,10 +38,12 @@ SIGNATURES: Dict[str, tuple] = {
     "desmo_workspace_bytes": (C.c_int, [_SP, C.POINTER(C.c_size_t)]),
     "desmo_build_w": (C.c_int, [_SP] + [_vp] * 8),
     "desmo_fused_residual_grad": (C.c_int, [_SP] + [_vp] * 9),
+    "desmo_recon_backward": (C.c_int, [_SP] + [_vp] * 9),
     "desmo_adamax_update": (C.c_int, [_SP] + [_vp] * 26),
     "desmo_assemble_grads": (C.c_int, [_SP] + [_vp] * 17),
     "desmo_reconstruct": (C.c_int, [_SP] + [_vp] * 6),
     "desmo_library_colnorm2": (C.c_int, [_SP] + [_vp] * 5),
+    "desmo_term_norms": (C.c_int, [_SP, _vp, _vp, _vp, _i32, _vp, _vp]),
     "desmo_last_fused_kernel_ms": (C.c_int, [C.POINTER(C.c_float)]),
     "desmo_debug_timers": (C.c_int, [_SP, _vp, _vp, _i32]),
     "desmo_pod_gram": (C.c_int, [_SP] + [_vp] * 4),

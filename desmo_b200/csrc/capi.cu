@@ -169,21 +169,31 @@ int desmo_build_w(const desmo_shape* s, const float* gates, float* rows, const f
                    step_dev, ws.l1, (cudaStream_t)stream);
 }
 
-int desmo_fused_residual_grad(const desmo_shape* s, const float* U, const float* P, const float* phi, const float* omega,
-                              const float* W, float* dphi, float* red, void* workspace, void* stream) {
+static int fused_dispatch(const desmo_shape* s, const float* U, const float* P, const float* phi, const float* omega, const float* W,
+                          float* dphi, float* red, void* workspace, void* stream, bool supplied, const char* who) {
     Dims d;
     int rc = validate_shape(s, &d);
     if (rc) return rc;
     if ((rc = device_ok())) return rc;
-    if (!U || !P || !phi || !omega || !W || !dphi || !red || !workspace) { set_error("desmo_fused_residual_grad: null pointer"); return DESMO_ERR_ARG; }
+    if (!U || !P || !phi || !omega || !W || !dphi || !red || !workspace) { set_error("%s: null pointer", who); return DESMO_ERR_ARG; }
     Workspace ws;
     if ((rc = carve_workspace(s, d, workspace, &ws))) return rc;
     if (s->path == DESMO_PATH_TC && !fused_tc_supported(s, d.Kp)) {
         set_error("tcgen05 path does not support this shape (Kp=%d, mld=%d)", d.Kp, s->mld);
         return DESMO_ERR_UNSUPPORTED;
     }
-    if (use_tc_path(s, d)) return fused_tc(s, d.mt, d.T, d.Kp, U, P, phi, omega, W, dphi, red, ws, (cudaStream_t)stream);
-    return fused_fp32(s, d.mt, d.T, d.Kp, U, P, phi, omega, W, dphi, red, ws, (cudaStream_t)stream);
+    if (use_tc_path(s, d)) return fused_tc(s, d.mt, d.T, d.Kp, U, P, phi, omega, W, dphi, red, ws, (cudaStream_t)stream, supplied);
+    return fused_fp32(s, d.mt, d.T, d.Kp, U, P, phi, omega, W, dphi, red, ws, (cudaStream_t)stream, supplied);
+}
+
+int desmo_fused_residual_grad(const desmo_shape* s, const float* U, const float* P, const float* phi, const float* omega,
+                              const float* W, float* dphi, float* red, void* workspace, void* stream) {
+    return fused_dispatch(s, U, P, phi, omega, W, dphi, red, workspace, stream, false, "desmo_fused_residual_grad");
+}
+
+int desmo_recon_backward(const desmo_shape* s, const float* grad_recon, const float* P, const float* phi, const float* omega,
+                         const float* W, float* dphi, float* red, void* workspace, void* stream) {
+    return fused_dispatch(s, grad_recon, P, phi, omega, W, dphi, red, workspace, stream, true, "desmo_recon_backward");
 }
 
 static int fill_update(const desmo_shape* s, const Dims& d, const Workspace& ws, UpdateArgs* a) {
@@ -266,11 +276,22 @@ int desmo_library_colnorm2(const desmo_shape* s, const float* P, const float* ph
     int rc = validate_shape(s, &d);
     if (rc) return rc;
     if ((rc = device_ok())) return rc;
-    if (!P || !phi || !omega || !out_k) { set_error("desmo_library_colnorm2: null pointer"); return DESMO_ERR_ARG; }
+    if (!phi || !omega || !out_k) { set_error("desmo_library_colnorm2: null pointer"); return DESMO_ERR_ARG; }
     EvalArgs a{};
     a.P = P; a.phi = phi; a.omega = omega; a.out = out_k; a.n = s->n; a.ld = s->ld; a.m = s->m; a.mld = s->mld;
     a.r = s->r; a.T = d.T; a.K = d.K; a.mt = d.mt;
     return launch_colnorm2(a, (cudaStream_t)stream);
+}
+
+int desmo_term_norms(const desmo_shape* s, const float* g2, const float* gates, const float* rows, int32_t fourier_quirk,
+                     double* norms_out, void* stream) {
+    Dims d;
+    int rc = validate_shape(s, &d);
+    if (rc) return rc;
+    if ((rc = device_ok())) return rc;
+    if (!g2 || !gates || !rows || !norms_out) { set_error("desmo_term_norms: null pointer"); return DESMO_ERR_ARG; }
+    if (fourier_quirk && d.T > s->m) { set_error("desmo_term_norms: the Fourier scripts' poly_norm reads time index i for term i: needs T <= m"); return DESMO_ERR_ARG; }
+    return launch_term_norms(g2, gates, rows, d.T, d.K, s->m, s->mld, fourier_quirk, norms_out, (cudaStream_t)stream);
 }
 
 int desmo_last_fused_kernel_ms(float* ms) {

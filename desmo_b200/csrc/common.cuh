@@ -73,10 +73,11 @@ struct EvalArgs {
 // host-side launchers (one per translation unit)
 int build_w(const desmo_shape* s, int K, int Kp, const float* gates, float* rows, const float* coefs, const float* periods,
             float* W, float* Whi, float* Wlo, int32_t* step_dev, float* l1_out, cudaStream_t st);
+// supplied = true: U holds dL/drecon ([m][ld]) and R := (n_global m / 2) * U instead of G W - U (desmo_recon_backward)
 int fused_fp32(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const float* U, const float* P, const float* phi,
-               const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st);
+               const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st, bool supplied = false);
 int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const float* U, const float* P, const float* phi,
-             const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st);
+             const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st, bool supplied = false);
 int fused_tc_supported(const desmo_shape* s, int Kp);
 int tc_debug_read(uint64_t* out, int count);
 int fused_event_ms(float* ms);
@@ -84,6 +85,8 @@ void fused_event_record(int which, cudaStream_t st);
 int launch_update(const UpdateArgs& a, cudaStream_t st);
 int launch_reconstruct(const EvalArgs& a, cudaStream_t st);
 int launch_colnorm2(const EvalArgs& a, cudaStream_t st);
+int launch_term_norms(const float* g2, const float* gates, const float* rows, int T, int K, int m, int mld, int fourier_quirk, double* out,
+                      cudaStream_t st);
 int pod_gram_fp32(const desmo_shape* s, const float* U, float* C, cudaStream_t st);
 int pod_gram_tc(const desmo_shape* s, const float* U, float* C, void* workspace, cudaStream_t st);
 int pod_eig(int m, int r, const float* C, float* V, float* sigma, void* workspace, size_t workspace_bytes, cudaStream_t st);

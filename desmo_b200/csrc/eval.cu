@@ -5,8 +5,8 @@
 namespace desmo {
 
 __device__ __forceinline__ void library_row_to_smem(const EvalArgs& a, long long x, int tid, float* Phi_s, float* G_s) {
-    for (int i = 0; i < a.r; ++i)
-        Phi_s[i * 256 + tid] = (x < a.ld) ? a.phi[(long long)i * a.ld + x] * a.P[(long long)i * a.ld + x] : 0.0f;
+    for (int i = 0; i < a.r; ++i)  // P == nullptr: the library of the raw phi_list, as the reference's post-hoc norms evaluate it (CYL:1192-1194)
+        Phi_s[i * 256 + tid] = (x < a.ld) ? (a.P ? a.phi[(long long)i * a.ld + x] * a.P[(long long)i * a.ld + x] : a.phi[(long long)i * a.ld + x]) : 0.0f;
     for (int j = 0; j < a.K; ++j) {
         float v;
         if (j < a.T) {
@@ -49,6 +49,38 @@ __global__ void __launch_bounds__(256) colnorm2_kernel(const EvalArgs a) {
             if ((tid & 31) == 0) atomicAdd(a.out + k, s);
         }
     }
+}
+
+// Post-hoc term norms (poly_norm / nonlinear_norm, CYL:624-692; FCYL:644-720) in closed form:
+//   norm_j = |gate_j| * ||G_j||_2 * ||z_j||_2       (= torch.norm(gate * (G_j z_j^T)), never materialising the n x m term)
+// fourier_quirk: the Fourier scripts stack the polynomial series as (T, m) but slice `zs[:, i:i+1]` (FCYL:652,659), so polynomial
+// term i < T is weighted by sqrt(sum_{j<T} z_j(t_i)^2) -- all T series at time index i -- instead of its own series' norm.
+__global__ void __launch_bounds__(256) term_norms_kernel(const float* __restrict__ g2, const float* __restrict__ gates,
+                                                         const float* __restrict__ rows, int T, int K, int m, int mld, int fourier_quirk,
+                                                         double* __restrict__ out) {
+    __shared__ double sh[8];
+    const int k = blockIdx.x, tid = threadIdx.x;
+    double acc = 0.0;
+    if (fourier_quirk && k < T) {
+        for (int j = tid; j < T; j += 256) { const double v = rows[(long long)j * mld + k]; acc += v * v; }
+    } else {
+        for (int t = tid; t < m; t += 256) { const double v = rows[(long long)k * mld + t]; acc += v * v; }
+    }
+    acc = warp_sum(acc);
+    if ((tid & 31) == 0) sh[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += sh[w];
+        out[k] = fabs((double)gates[k]) * sqrt((double)g2[k]) * sqrt(s);
+    }
+}
+
+int launch_term_norms(const float* g2, const float* gates, const float* rows, int T, int K, int m, int mld, int fourier_quirk, double* out,
+                      cudaStream_t st) {
+    term_norms_kernel<<<K, 256, 0, st>>>(g2, gates, rows, T, K, m, mld, fourier_quirk, out);
+    DESMO_CUDA(cudaGetLastError());
+    return DESMO_OK;
 }
 
 int launch_reconstruct(const EvalArgs& a, cudaStream_t st) {

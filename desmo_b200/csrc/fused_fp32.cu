@@ -31,6 +31,7 @@ struct FusedArgs {
     long long n, ld;
     int m, mld, r, T, K, nchunk, mc;
     float scale;  // 2 / (n_global * m)
+    float seed_scale;  // > 0: U holds dL/drecon and R := seed_scale * U instead of G W - U (desmo_recon_backward)
     MonoTable mt;
 };
 
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(kTile, 1) fused_fp32_kernel(const FusedArgs a)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int t = t0 + tg * 4 + j;
-                    rr[j] = (xin && t < a.m) ? rec[j] - u[tg * 4 + j] : 0.0f;
+                    rr[j] = (xin && t < a.m) ? (a.seed_scale > 0.0f ? a.seed_scale * u[tg * 4 + j] : rec[j] - u[tg * 4 + j]) : 0.0f;
                     lsum = fmaf(rr[j], rr[j], lsum);
                     R_s[(tg * 4 + j) * kGS + tid] = rr[j];
                 }
@@ -469,7 +470,7 @@ static int launch_fused(const FusedArgs& a, int sms, size_t smem_cap, cudaStream
 }
 
 int fused_fp32(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const float* U, const float* P, const float* phi,
-               const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st) {
+               const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st, bool supplied) {
     int dev = 0, sms = 0, smem_cap = 0;
     DESMO_CUDA(cudaGetDevice(&dev));
     DESMO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -479,6 +480,7 @@ int fused_fp32(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const f
     a.Epart = ws.Epart; a.Spart = ws.Spart; a.Dacc = ws.Dacc;
     a.n = s->n; a.ld = s->ld; a.m = s->m; a.mld = s->mld; a.r = s->r; a.T = T; a.K = T + 3 * s->r;
     a.scale = (float)(2.0 / ((double)s->n_global * (double)s->m));
+    a.seed_scale = supplied ? (float)(0.5 * (double)s->n_global * (double)s->m) : 0.0f;
     a.mt = mt;
     int gx = 0, nslots = 0, rc = 0;
     switch (Kp) {

@@ -6,9 +6,9 @@
 //   G1  Rec[p x t]    = G[p x lib] W[lib x t]           -> TMEM cols [0,128)                      (CYL:548,565-572)
 //   epi r = Rec - U   (U read once from HBM: 24 of a quarter's 32 snapshots through a private TMA ring, 8 by prefetching loads;
 //       R never leaves the SM) (CYL:722); sum r^2;
-//       r -> three bf16 planes (formed in registers before R_s is free), then R_s[p rows][t contiguous] in shared memory
+//       r -> NPR (= 2) bf16 planes (formed in registers before R_s is free), then R_s[p rows][t contiguous] in shared memory
 //       (128B-swizzled: K-major operand of G3 AND MN-major operand of G4)
-//   G3  D[p x lib]   += R[p x t] W^T[t x lib]           -> TMEM cols [128,224): three N-stacked blocks, accumulated over the slabs
+//   G3  D[p x lib]   += R[p x t] W^T[t x lib]           -> TMEM cols [128,128+32*NPR): N-stacked blocks, accumulated over the slabs
 //   G4  E^T[t x lib] += R^T[t x p] G[p x lib]           -> TMEM cols [256+32*slab, +32), accumulated over the tiles of the CTA and
 //       drained every 32 tiles into the CTA's fp32 partial (the tensor core truncates when it adds into the accumulator)
 // Warp roles (20 warps): warp 0 = TMA producer (W slab planes), warp 1 = MMA issuer (one elected thread), warps 2-3 = TMA
@@ -43,25 +43,44 @@ constexpr uint32_t W_BOX = 3 * KP * 128;              // W slab box: [3 planes x
 constexpr uint32_t W_PLANE = KP * 128;                // row offset of a plane inside a box
 constexpr uint32_t W_SLAB = 2 * W_BOX;                // two boxes (snapshots 0-63, 64-127)
 constexpr uint32_t G_PLANE = 2 * KP * 128;            // one bf16 plane of G: 2 boxes [32 lib rows x 128 B (64 p)]
+// Planes of R (and of the W / G operands that multiply it) used by the two gradient GEMMs G3 / G4.  Two bf16 planes carry 16
+// significand bits; with the three products R1*X1 + R1*X2 + R2*X1 the gradients come out at ~3e-7 relative (measured against an
+// fp64 evaluation on the golden cases: 2e-7 .. 1.4e-6, the same class as a plain fp32 GEMM), far inside the 1e-5 gate, while Rec = G W
+// keeps all three planes (R is a small difference of large numbers).  DESMO_NPR=3 restores the six-product gradients.
+#ifndef DESMO_NPR
+#define DESMO_NPR 2
+#endif
+constexpr int NPR = DESMO_NPR;
+static_assert(NPR == 2 || NPR == 3, "R planes");
 constexpr uint32_t R_OFF = 0;
-constexpr uint32_t W_OFF = R_OFF + 3 * R_PLANE;        // 98304
-constexpr uint32_t G_OFF = W_OFF + 2 * W_SLAB;         // 147456
+constexpr uint32_t W_OFF = R_OFF + NPR * R_PLANE;
+constexpr uint32_t G_OFF = W_OFF + 2 * W_SLAB;
 // U staging: each snapshot quarter of the epilogue owns a private ring of 3 TMA stages of [8 snapshots][128 points] fp32.
 // Private rings matter: mbarrier parity waits are only sound if a waiter is never two phases away from the barrier, which a
 // ring shared by independently progressing consumer groups cannot guarantee.
-constexpr uint32_t U_OFF = G_OFF + 3 * G_PLANE;        // 172032
+constexpr uint32_t U_OFF = G_OFF + 3 * G_PLANE;
 #ifndef DESMO_U_ROWS
 #define DESMO_U_ROWS 8
 #endif
 constexpr int U_ROWS = DESMO_U_ROWS;  // snapshots per TMA stage
 constexpr uint32_t U_STAGE = U_ROWS * BP * 4;          // 4096 (must be a multiple of 128 B, the TMA destination alignment)
-constexpr int U_STAGES = 3;                            // per quarter
+#ifndef DESMO_U_STAGES
+#define DESMO_U_STAGES 3
+#endif
+constexpr int U_STAGES = DESMO_U_STAGES;               // per quarter
 constexpr int U_TAIL = QT - U_STAGES * U_ROWS;         // snapshots of a quarter fetched by the epilogue threads themselves (registers)
-constexpr uint32_t RED_OFF = U_OFF + NQ * U_STAGES * U_STAGE;  // 221184  (4 quadrants x kScal doubles)
+// Experiment hook: TMA L2-prefetches of U issued by the producer threads U_PREFETCH slab-tiles ahead of the ring.  Measured (round 2,
+// profiles/README.md): 5200 -> 5650-6170 cycles per slab-tile for distances 1-4, i.e. slower -- the prefetches queue in the same TMA
+// unit as the ring's loads -- so the default is off.
+#ifndef DESMO_U_PREFETCH
+#define DESMO_U_PREFETCH 0
+#endif
+constexpr int U_PREFETCH = DESMO_U_PREFETCH;
+constexpr uint32_t RED_OFF = U_OFF + NQ * U_STAGES * U_STAGE;  // (4 quadrants x kScal doubles)
 constexpr uint32_t SMEM_BYTES = RED_OFF + 4 * kScal * 8 + 1024;  // + alignment slack
 static_assert(SMEM_BYTES + 1024 <= 232448, "dynamic + static shared memory must fit the 227 KB of an sm_100 CTA");
 static_assert(U_TAIL >= 0 && U_STAGE % 128 == 0, "U stage shape");
-constexpr uint32_t TMEM_REC = 0, TMEM_D = 128, TMEM_E = 256;  // D: 3 column blocks of 32 (N-stacked B planes), summed in the epilogue
+constexpr uint32_t TMEM_REC = 0, TMEM_D = 128, TMEM_E = 256;  // D: NPR column blocks of 32 (N-stacked B planes), summed in the epilogue
 }  // namespace tc
 
 struct TcArgs {
@@ -77,6 +96,7 @@ struct TcArgs {
     int m, mld, r, T, K, nslab, kp_out;
     unsigned long long* dbg;  // optional per-CTA phase timers (cycles), 32 per CTA
     float scale;
+    float seed_scale;  // kSupplied: factor applied to the supplied upstream gradient (n_global * m / 2, undoing the MSE scale downstream)
     MonoTable mt;
 };
 
@@ -118,6 +138,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -172,22 +195,36 @@ __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t& w1, ui
     const float f0 = e0 - __uint_as_float(w2 << 16), f1 = e1 - __uint_as_float(w2 & 0xffff0000u);
     asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w3) : "f"(f1), "f"(f0));
 }
+__device__ __forceinline__ void split2_pair(float x0, float x1, uint32_t& w1, uint32_t& w2) {
+    asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w1) : "f"(x1), "f"(x0));
+    const float e0 = x0 - __uint_as_float(w1 << 16), e1 = x1 - __uint_as_float(w1 & 0xffff0000u);
+    asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w2) : "f"(e1), "f"(e0));
+}
 
 // The six (a-plane, b-plane) products kept by the 3-way split (i + j <= 4), smallest contributions first.
 // Descriptors: the high word is constant per operand role; the low word is (addr >> 4) | (LBO >> 4) << 16, so stepping through
 // planes / k-steps is ONE 32-bit add of a compile-time constant per operand (smem addresses < 256 KB never carry out of 14 bits).
 #define DESMO_PAIRS(X) X(2, 0) X(0, 2) X(1, 1) X(1, 0) X(0, 1) X(0, 0)
+#if DESMO_NPR == 3
+#define DESMO_GRAD_PAIRS(X) DESMO_PAIRS(X)
+#else
+#define DESMO_GRAD_PAIRS(X) X(1, 0) X(0, 1) X(0, 0)
+#endif
 __device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
 
-template <bool kDebug>
+// kSupplied: backward of forward()'s reconstruction for an arbitrary upstream gradient (desmo_recon_backward): the buffer read through
+// the U path holds dL/drecon, R := seed_scale * (that) instead of G W - U, G1 is skipped; G3 / G4 / hand-overs are unchanged.
+template <bool kDebug, bool kSupplied>
 __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmW,
-                                                                          const __grid_constant__ CUtensorMap tmU) {
+                                                                          const __grid_constant__ CUtensorMap tmU,
+                                                                          const __grid_constant__ CUtensorMap tmUp) {
     using namespace tc;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[44];
+    __shared__ __align__(8) uint64_t bars[12 + 2 * tc::NQ * tc::U_STAGES + 4];
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t sink_s[32];  // write-only (see the epilogue)
+    __shared__ float omega_s[3 * kMaxR];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     double* red_s = reinterpret_cast<double*>(smem + RED_OFF);
@@ -216,6 +253,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = tid; i < 4 * kScal; i += THREADS) red_s[i] = 0.0;
+    if (tid < 3 * a.r) omega_s[tid] = a.omega[tid];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -246,7 +284,20 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             long long tile = blockIdx.x;
             unsigned long long tp0 = 0;
             const long long tps = now();
+            // L2 prefetch cursor, U_PREFETCH slab-tiles ahead of the ring (one [32 snapshots][128 points] box per quarter)
+            int pslab = 0, pit = 0;
+            long long ptile = blockIdx.x;
+            auto prefetch_next = [&]() {
+                if (U_PREFETCH == 0 || pit >= total) return;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) tma_prefetch_2d(&tmUp, (int)(ptile * BP), pslab * BT + (h0 + hh) * QT);
+                ++pit;
+                if (++pslab == nslab) { pslab = 0; ptile += gridDim.x; }
+            };
+            if (U_PREFETCH > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmUp) : "memory");
+            for (int i = 0; i < U_PREFETCH; ++i) prefetch_next();
             for (int it = 0; it < total; ++it) {
+                prefetch_next();
 #pragma unroll
                 for (int k = 0; k < U_STAGES; ++k)
 #pragma unroll
@@ -294,7 +345,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         acc = 1;                                                                                                      \
     }
 #ifndef EXP_NO_G1
-                DESMO_PAIRS(G1_PAIR)
+                if (!kSupplied) { DESMO_PAIRS(G1_PAIR) }
 #endif
 #undef G1_PAIR
                 umma_commit(bar(REC_FULL));
@@ -318,12 +369,15 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
 #define G3_PLANE(PA)                                                                                                 \
     _Pragma("unroll") for (int ks = 0; ks < BT / 16; ++ks) {                                                          \
         mma_bf16(tmem + TMEM_D, desc_from(rk_lo + ((PA * R_PLANE + (ks >> 2) * (BP * 128) + (ks & 3) * 32) >> 4), kDescHi), \
-                 desc_from(wk_lo + (((ks >> 2) * W_BOX + (ks & 3) * 32) >> 4), kDescHi), make_idesc_bf16(BP, KP * (3 - PA), 0, 0), \
+                 desc_from(wk_lo + (((ks >> 2) * W_BOX + (ks & 3) * 32) >> 4), kDescHi), make_idesc_bf16(BP, KP * (NPR - PA), 0, 0), \
                  (PA == 0) ? acc0 : 1u);                                                                              \
         if (PA == 0) acc0 = 1;                                                                                        \
     }
 #ifndef EXP_NO_G3
-                G3_PLANE(0) G3_PLANE(1) G3_PLANE(2)
+                G3_PLANE(0) G3_PLANE(1)
+#if DESMO_NPR == 3
+                G3_PLANE(2)
+#endif
 #endif
 #undef G3_PLANE
                 umma_commit(bar(W_EMPTY0 + buf));  // W slab is dead after G3: let the producer refill it while G4 runs
@@ -343,7 +397,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
 #ifndef EXP_NO_G4
-                    DESMO_PAIRS(G4_PAIR)
+                    DESMO_GRAD_PAIRS(G4_PAIR)
 #endif
                     umma_commit(bar(R_EMPTYQ0 + qq));
                 }
@@ -382,7 +436,12 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             uint32_t v0[8], v1[8], v2[8];
             tmem_ld8(tmem + lane_addr + TMEM_D + h * 8, v0);
             tmem_ld8(tmem + lane_addr + TMEM_D + KP + h * 8, v1);
-            tmem_ld8(tmem + lane_addr + TMEM_D + 2 * KP + h * 8, v2);
+            if (NPR == 3) {
+                tmem_ld8(tmem + lane_addr + TMEM_D + 2 * KP + h * 8, v2);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v2[j] = 0u;
+            }
             tmem_ld_wait();
             if ((tile_local + 1) % E_FLUSH_TILES == 0 || tile_local == my_tiles - 1) {
                 // E^T accumulators -> this CTA's fp32 partial (round-to-nearest adds), then the MMA issuer restarts them at zero
@@ -412,7 +471,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                if (h * 8 + j < a.kp_out)
+                if (h * 8 + j < a.K)  // rows K..Kp-1 of D belong to zero rows of W: never read by the chain rule
                     a.Dacc[(long long)(h * 8 + j) * a.ld + x] = (__uint_as_float(v2[j]) + __uint_as_float(v1[j])) + __uint_as_float(v0[j]);
             // the accumulator is handed back only after the loaded registers were consumed: an experiment that arrived on REC_EMPTY
             // straight after tcgen05.wait::ld (before using the data) produced wrong residuals in a few columns (profiles/README.md)
@@ -425,9 +484,19 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         //      so only the split + 24 two-byte stores sit between "G_s free" and "G_s full" at a tile boundary.  Rolled loops on
         //      purpose (gv[] lives in local memory): this runs once per tile and straight-line code only thrashes the I-cache. ----
         float gv[KP / NQ];
+        unsigned long long tl2[2] = {0, 0};
+        auto prefetch_lat = [&](long long tile_) {  // phi / P of a later tile -> L2, a tile ahead of their use (quarter h takes modes h, h+4)
+            const long long x_ = tile_ * BP + p;
+            for (int i = h; i < a.r; i += NQ) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.phi + (long long)i * a.ld + x_));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.P + (long long)i * a.ld + x_));
+            }
+        };
         auto eval_library = [&](long long tile_) {
             const long long x_ = tile_ * BP + p;
+            const long long ce0 = now();
             for (int i = 0; i < a.r; ++i) lat[i] = a.phi[(long long)i * a.ld + x_] * a.P[(long long)i * a.ld + x_];
+            const long long ce1 = now();
 #pragma unroll 1
             for (int jj = 0; jj < KP / NQ; ++jj) {
                 const int j = h + jj * NQ;
@@ -436,11 +505,12 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                     v = monomial(a.mt, j, lat, 1);
                 } else if (j < a.K) {
                     const int b = (j - a.T) / a.r, i = (j - a.T) - b * a.r;
-                    const float arg = a.omega[3 * i + b] * lat[i];
+                    const float arg = omega_s[3 * i + b] * lat[i];
                     v = (b == 0) ? sinf(arg) : (b == 1) ? cosf(arg) : tanhf(arg);
                 }
                 gv[jj] = v;
             }
+            if (kDebug) { tl2[0] += ce1 - ce0; tl2[1] += now() - ce1; }
         };
         auto store_library = [&]() {  // three bf16 planes, G_s[lib rows][p contiguous]
             const uint32_t gs = sbase + G_OFF + (p >> 6) * (KP * 128);
@@ -468,6 +538,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             const bool xin = x < a.n;
             long long cg0 = now();
             if (tl == 0) eval_library(tile);
+            if (tl + 1 < my_tiles) prefetch_lat(tile + gridDim.x);
             long long cg1 = now();
             if (tl > 0) mbar_wait(bar(G_EMPTY), (tl - 1) & 1, 9, tl);
             cg0 = now(); te[5] += cg0 - cg1;
@@ -476,8 +547,9 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             if (tl > 0) store_d(tl - 1, tile - gridDim.x);
 
             float lsum = 0.0f;  // fp32 over the 256 residuals of a tile, folded into the fp64 accumulator once per tile (FP64 adds are slow)
-            float ulast[U_TAIL];
+            float ulast[U_TAIL > 0 ? U_TAIL : 1];
             auto load_last = [&](int slab2) {  // snapshots 24..31 of this thread's quarter, straight from HBM/L2
+                if (U_TAIL == 0) return;
                 const int tb = slab2 * BT + h * QT + U_STAGES * U_ROWS;
                 const float* up = a.U + (long long)tb * a.ld + x;
                 if (xin && tb + U_TAIL <= a.m) {
@@ -496,10 +568,12 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 long long c1 = now(); te[0] += c1 - c0;
                 tc_fence_after();
                 uint32_t u[QT];  // Rec of this thread's 32 snapshots, then r = Rec - U in place
-                tmem_ld16(tmem + lane_addr + TMEM_REC + h * QT, u);
-                tmem_ld16(tmem + lane_addr + TMEM_REC + h * QT + 16, u + 16);
+                if (!kSupplied) {
+                    tmem_ld16(tmem + lane_addr + TMEM_REC + h * QT, u);
+                    tmem_ld16(tmem + lane_addr + TMEM_REC + h * QT + 16, u + 16);
+                }
                 mbar_wait(bar(U_FULL0 + h * U_STAGES), it & 1, 11, it);
-                tmem_ld_wait();
+                if (!kSupplied) tmem_ld_wait();
 #ifdef EXP_EARLY_REC
 #ifdef EXP_EARLY_REC_DEP
                 {
@@ -527,7 +601,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
 #else
                             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(uv) : "r"(us + j * (BP * 4)));
 #endif
-                            float rr = __uint_as_float(u[k * U_ROWS + j]) - uv;
+                            float rr = kSupplied ? uv * a.seed_scale : __uint_as_float(u[k * U_ROWS + j]) - uv;
                             if (decltype(masked)::value) rr = (xin && t0 + k * U_ROWS + j < a.m) ? rr : 0.0f;
                             u[k * U_ROWS + j] = __float_as_uint(rr);
                             lsum = fmaf(rr, rr, lsum);
@@ -546,7 +620,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                     }
 #pragma unroll
                     for (int j = 0; j < U_TAIL; ++j) {  // last snapshots of the quarter: prefetched into registers one slab ago
-                        float rr = __uint_as_float(u[U_STAGES * U_ROWS + j]) - ulast[j];
+                        float rr = kSupplied ? ulast[j] * a.seed_scale : __uint_as_float(u[U_STAGES * U_ROWS + j]) - ulast[j];
                         if (decltype(masked)::value) rr = (xin && t0 + U_STAGES * U_ROWS + j < a.m) ? rr : 0.0f;
                         u[U_STAGES * U_ROWS + j] = __float_as_uint(rr);
                         lsum = fmaf(rr, rr, lsum);
@@ -559,17 +633,19 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
 #endif
                 // ---- r -> three bf16 planes, formed in REGISTERS while G3/G4 of the previous slab still read R_s: only the 12 vector
                 //      stores below sit between "R_s free" and "R_s full", i.e. on the tensor pipe's critical path ----
-                uint32_t w1[16], w2[16], w3[16];
+                uint32_t w1[16], w2[16], w3[NPR == 3 ? 16 : 1];
 #pragma unroll
-                for (int ee = 0; ee < 16; ++ee)
-                    split3_pair(__uint_as_float(u[2 * ee]), __uint_as_float(u[2 * ee + 1]), w1[ee], w2[ee], w3[ee]);
+                for (int ee = 0; ee < 16; ++ee) {
+                    if (NPR == 3) split3_pair(__uint_as_float(u[2 * ee]), __uint_as_float(u[2 * ee + 1]), w1[ee], w2[ee], w3[NPR == 3 ? ee : 0]);
+                    else split2_pair(__uint_as_float(u[2 * ee]), __uint_as_float(u[2 * ee + 1]), w1[ee], w2[ee]);
+                }
                 {
                     // ptxas sinks pure arithmetic below the wait loop to shorten live ranges, which would put the whole split back on
-                    // the critical path: consuming every third-plane word (each depends on its first- and second-plane words) in a
+                    // the critical path: consuming every last-plane word (each depends on the words of the planes before it) in a
                     // store that precedes the wait pins the split where it is written.  8 LOP3 + 1 STS per thread and slab.
                     uint32_t x = 0;
 #pragma unroll
-                    for (int ee = 0; ee < 16; ++ee) x ^= w3[ee];
+                    for (int ee = 0; ee < 16; ++ee) x ^= (NPR == 3) ? w3[NPR == 3 ? ee : 0] : w2[ee];
                     asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(&sink_s[lane])), "r"(x) : "memory");
                 }
                 c0 = now(); te[1] += c0 - c1;
@@ -585,7 +661,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                     const uint32_t off = ((uint32_t)(((h & 1) * 4 + c) ^ (p & 7))) << 4;
                     st_shared_v4(rs + off, w1[4 * c], w1[4 * c + 1], w1[4 * c + 2], w1[4 * c + 3]);
                     st_shared_v4(rs + R_PLANE + off, w2[4 * c], w2[4 * c + 1], w2[4 * c + 2], w2[4 * c + 3]);
-                    st_shared_v4(rs + 2 * R_PLANE + off, w3[4 * c], w3[4 * c + 1], w3[4 * c + 2], w3[4 * c + 3]);
+                    if (NPR == 3) {
+                        constexpr int s3 = (NPR == 3) ? 4 : 0;
+                        st_shared_v4(rs + 2 * R_PLANE + off, w3[s3 * c], w3[s3 * c + (s3 ? 1 : 0)], w3[s3 * c + (s3 ? 2 : 0)], w3[s3 * c + (s3 ? 3 : 0)]);
+                    }
                 }
                 c0 = now(); te[4] += c0 - c1;
                 fence_async_smem();
@@ -600,6 +679,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         if (a.dbg && tid == 128) {
             for (int i = 0; i < 8; ++i) a.dbg[blockIdx.x * 32 + 8 + i] = te[i];
             a.dbg[blockIdx.x * 32 + 16] = now() - tstart;
+            a.dbg[blockIdx.x * 32 + 24] = tl2[0];
+            a.dbg[blockIdx.x * 32 + 25] = tl2[1];
         }
         if (a.dbg && lane == 0 && blockIdx.x == 0)
             for (int i = 0; i < 8; ++i) a.dbg[8192 + e * 8 + i] = te[i];
@@ -671,7 +752,7 @@ int chain_rule_launch(const desmo_shape* s, const MonoTable& mt, int T, int Kp, 
                       const Workspace& ws, int slot_base, int* nslots, cudaStream_t st);
 
 int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const float* U, const float* P, const float* phi,
-             const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st) {
+             const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st, bool supplied) {
     (void)W;
     if (!fused_tc_supported(s, Kp)) { set_error("tcgen05 path: unsupported shape"); return DESMO_ERR_UNSUPPORTED; }
     EncodeTiledFn enc = encode_fn();
@@ -697,6 +778,15 @@ int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const flo
                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(U) failed (%d)", (int)cr); return DESMO_ERR_CUDA; }
     }
+    CUtensorMap tmup;  // L2-prefetch box: one quarter of a slab-tile
+    {
+        const cuuint64_t udims[2] = {(cuuint64_t)s->ld, (cuuint64_t)s->m};
+        const cuuint64_t ustr[1] = {(cuuint64_t)s->ld * 4};
+        const cuuint32_t ubox[2] = {(cuuint32_t)tc::BP, (cuuint32_t)tc::QT};
+        cr = enc(&tmup, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)U, udims, ustr, ubox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(U prefetch) failed (%d)", (int)cr); return DESMO_ERR_CUDA; }
+    }
     TcArgs a{};
     a.U = U; a.P = P; a.phi = phi; a.omega = omega; a.dphi = dphi; a.Epart = ws.Epart; a.Spart = ws.Spart; a.Dacc = ws.Dacc;
     a.n = s->n; a.ld = s->ld; a.m = s->m; a.mld = s->mld; a.r = s->r; a.T = T; a.K = T + 3 * s->r;
@@ -714,16 +804,20 @@ int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const flo
     }
     a.kp_out = Kp;
     a.scale = (float)(2.0 / ((double)s->n_global * (double)s->m));
+    a.seed_scale = (float)(0.5 * (double)s->n_global * (double)s->m);
     a.mt = mt;
     const long long ntiles = s->ld / tc::BP;
     const int grid = (int)(ntiles < sms ? ntiles : sms);
     fused_event_record(0, st);
-    if (a.dbg) {
-        DESMO_CUDA(cudaFuncSetAttribute(fused_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-        fused_tc_kernel<true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, tm, tmu);
+    if (supplied) {
+        DESMO_CUDA(cudaFuncSetAttribute(fused_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+        fused_tc_kernel<false, true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, tm, tmu, tmup);
+    } else if (a.dbg) {
+        DESMO_CUDA(cudaFuncSetAttribute(fused_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+        fused_tc_kernel<true, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, tm, tmu, tmup);
     } else {
-        DESMO_CUDA(cudaFuncSetAttribute(fused_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-        fused_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, tm, tmu);
+        DESMO_CUDA(cudaFuncSetAttribute(fused_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+        fused_tc_kernel<false, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, tm, tmu, tmup);
     }
     fused_event_record(1, st);
     DESMO_CUDA(cudaGetLastError());

@@ -7,7 +7,7 @@
 namespace desmo {
 
 // ---------------------------------------------------------------------------------------------------------------
-// Gram, FFMA version (the tcgen05 TF32x3 version lives in gram_tc.cu): 64x64 output tile per CTA, split over points.
+// Gram, FFMA version (the tcgen05 version -- three bf16 planes per fp32 operand -- lives in gram_tc.cu): 64x64 output tile per CTA, split over points.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kGT = 64;   // output tile edge
 constexpr int kGX = 32;   // points per smem stage

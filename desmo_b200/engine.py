@@ -169,6 +169,39 @@ class DesmoEngine:
             g["rows"] = g["rows"][:, :self.m]
         return g
 
+    def recon_backward(self, grad_recon: torch.Tensor) -> dict:
+        """d L / d every packed parameter for an upstream gradient dL/drecon of shape (m, n) (autograd backward of forward()'s
+        recon, CYL:766): desmo_recon_backward (the fused G3 / G4 machinery with R supplied) + desmo_assemble_grads."""
+        if tuple(grad_recon.shape) != (self.m, self.n):
+            raise ValueError(f"grad_recon must be ({self.m}, {self.n}), got {tuple(grad_recon.shape)}")
+        f32 = dict(dtype=torch.float32, device=self.device)
+        gr = torch.zeros(self.m, self.ld, **f32)  # the layout of U: pitch ld, pad columns zero
+        gr[:, :self.n].copy_(grad_recon)
+        saved = list(self.hyper_host)
+        self.set_hyper(saved[:5], 0.0, 0.0)  # no regulariser terms: pure chain rule of the upstream gradient
+        g = {"gates": torch.zeros(self.K, **f32), "omega": torch.zeros(3 * self.r, **f32), "phi": torch.zeros(self.r, self.ld, **f32)}
+        if self.nF:
+            g["coefs"], g["periods"] = torch.zeros_like(self.coefs), torch.zeros_like(self.periods)
+        else:
+            g["rows"] = torch.zeros(self.K, self.mld, **f32)
+        losses = torch.zeros(4, **f32)
+        with torch.cuda.device(self.device):
+            self.build_w(False)
+            check(self.lib.desmo_recon_backward(C.byref(self.shape), _ptr(gr), _ptr(self.P), _ptr(self.phi), _ptr(self.omega),
+                                                _ptr(self.W), _ptr(self.dphi), _ptr(self.red), _ptr(self.workspace), self._stream()),
+                  "desmo_recon_backward")
+            self.all_reduce()
+            g["phi"].copy_(self.dphi)
+            check(self.lib.desmo_assemble_grads(
+                C.byref(self.shape), _ptr(self.red), _ptr(g["phi"]), _ptr(self.P), _ptr(self.phi), _ptr(self.gates), _ptr(self.rows),
+                _ptr(self.coefs), _ptr(self.periods), _ptr(self.hyper), _ptr(g["gates"]), _ptr(g.get("rows")), _ptr(g.get("coefs")),
+                _ptr(g.get("periods")), _ptr(g["omega"]), _ptr(losses), _ptr(self.workspace), self._stream()), "desmo_assemble_grads")
+        self.set_hyper(saved[:5], saved[5], saved[6])
+        g["phi"] = g["phi"][:, :self.n]
+        if "rows" in g:
+            g["rows"] = g["rows"][:, :self.m]
+        return g
+
     def reconstruct(self) -> torch.Tensor:
         """recon (m, n) -- first element of forward()'s tuple (CYL:576)."""
         out = torch.empty(self.m, self.ld, dtype=torch.float32, device=self.device)
@@ -178,17 +211,23 @@ class DesmoEngine:
                                              _ptr(out), self._stream()), "desmo_reconstruct")
         return out[:, :self.n]
 
-    def term_norms(self) -> torch.Tensor:
-        """||gate_j G_j z_j^T||_F = |gate_j| ||G_j|| ||z_j|| for every term (poly_norm / nonlinear_norm, CYL:624-692), K order."""
+    def term_norms(self, physical: bool = False) -> torch.Tensor:
+        """Per-term norms of the post-hoc sweep, K order, fp64 (poly_norm / nonlinear_norm, CYL:624-692; FCYL:644-720).
+
+        Default = the reference's semantics, which define the active mask: the scripts pass the RAW ``phi_list`` (CYL:1192-1194),
+        so the library is evaluated on phi alone, and the Fourier scripts weight polynomial term i by all T series at time index
+        i (FCYL:652,659).  ``physical=True`` returns ||gate_j G_j z_j^T||_F of the term as it enters forward() (phi * POD)."""
         g2 = torch.zeros(self.K, dtype=torch.float32, device=self.device)
+        out = torch.zeros(self.K, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
             self.build_w(False)  # refreshes rows for the Fourier variant
-            check(self.lib.desmo_library_colnorm2(C.byref(self.shape), _ptr(self.P), _ptr(self.phi), _ptr(self.omega), _ptr(g2),
-                                                  self._stream()), "desmo_library_colnorm2")
-        if self.n_global != self.n and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(g2, group=self.pg)
-        zn = torch.linalg.vector_norm(self.rows[:, :self.m].double(), dim=1)
-        return self.gates.abs().double() * g2.double().sqrt() * zn
+            check(self.lib.desmo_library_colnorm2(C.byref(self.shape), _ptr(self.P) if physical else None, _ptr(self.phi),
+                                                  _ptr(self.omega), _ptr(g2), self._stream()), "desmo_library_colnorm2")
+            if self.n_global != self.n and torch.distributed.is_initialized():
+                torch.distributed.all_reduce(g2, group=self.pg)
+            check(self.lib.desmo_term_norms(C.byref(self.shape), _ptr(g2), _ptr(self.gates), _ptr(self.rows),
+                                            1 if (self.nF and not physical) else 0, _ptr(out), self._stream()), "desmo_term_norms")
+        return out
 
     def residual_norm2(self) -> float:
         """||G W - U||_F^2 over all ranks with the current gates (evaluation pass, no update)."""

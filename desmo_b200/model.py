@@ -6,9 +6,15 @@ unchanged, and the shipped ``.pt`` files load with ``strict=True``).  Every ``nn
 packed device buffers, so kernel-side updates are visible through the module and vice versa.
 
 The reference reads ``POD_modes`` / ``device`` / ``t_points`` / ``period_init`` from module globals; here they are explicit
-keyword arguments (``pod_modes=...``).  ``forward(X)`` keeps the reference signature and returns the same 3-tuple, materialised
-for evaluation; training goes through ``DesmoTrainer.step()`` (fully fused) or ``model.mse_loss(snapshot)`` (autograd-visible
-loss whose backward is the fused kernel), neither of which ever forms the m x n reconstruction.
+keyword arguments (``pod_modes=...``).  ``forward(X)`` keeps the reference signature and returns the same 3-tuple; ``recon`` is
+materialised and carries a ``grad_fn`` whose backward runs the fused kernels on the upstream gradient (``desmo_recon_backward``),
+so the reference loop ``recon, lat, _ = model(snapshot); loss = criterion(recon, snapshot); total.backward(); optimizer.step()``
+(CYL:711-768) runs unmodified.  The fast paths are ``DesmoTrainer.step()`` (fully fused, no m x n tensor besides the snapshot)
+and ``model.mse_loss(snapshot)`` (autograd-visible loss whose backward is the fused pass).
+
+The reference's post-hoc sweep rebinds ``param.data = clone`` (CYL:1219-1226), which detaches a Parameter from the packed
+buffer it aliased; every entry point that launches kernels first calls ``sync_parameters()``, which copies such a Parameter's
+values back into the packed storage and re-aliases it, so that code runs unmodified too.
 """
 from __future__ import annotations
 
@@ -37,6 +43,21 @@ class _FusedMSE(torch.autograd.Function):
         for kind, idx in ctx.names:
             res.append(_slice_grad(eng, g, kind, idx) * grad_out)
         return (None, None, *res)
+
+
+class _FusedRecon(torch.autograd.Function):
+    """recon = forward()[0] (CYL:572-576), differentiable: backward(dL/drecon) = desmo_recon_backward + desmo_assemble_grads."""
+
+    @staticmethod
+    def forward(ctx, engine: DesmoEngine, names, *params):
+        ctx.engine, ctx.names = engine, names
+        return engine.reconstruct()
+
+    @staticmethod
+    def backward(ctx, grad_recon):
+        eng = ctx.engine
+        g = eng.recon_backward(grad_recon)
+        return (None, None, *[_slice_grad(eng, g, kind, idx) for kind, idx in ctx.names])
 
 
 def _slice_grad(eng: DesmoEngine, g: dict, kind: str, idx) -> torch.Tensor:
@@ -121,6 +142,47 @@ class _DesmoBase(nn.Module):
                                   "instead of moving / casting it (no CPU fallback)")
         return out
 
+    def _views(self):
+        """(Parameter, view of the packed buffer it must alias) for every parameter, registration order."""
+        e = self.engine
+        T, r = e.T, e.r
+        rows = e.coefs if e.nF else e.rows[:, :e.m]
+        yield self.c_coef, e.gates[:T]
+        for i in range(r):
+            yield self.phi_list[i], e.phi[i, :e.n]
+        for j in range(T):
+            yield self.z_list[j], rows[j]
+        if e.nF:
+            for j in range(T):
+                yield self.period_list[j], e.periods[j:j + 1]
+            for q in range(3 * r):
+                k = T + (q % 3) * r + q // 3
+                yield self.trig_period_list[q], e.periods[k:k + 1]
+        for b, (zl, cl) in enumerate(((self.zsin_list, self.sin_coef_list), (self.zcos_list, self.cos_coef_list),
+                                      (self.ztanh_list, self.tanh_coef_list))):
+            for i in range(r):
+                yield zl[i], rows[T + b * r + i]
+                yield cl[i], e.gates[T + b * r + i]
+        for i in range(3 * r):
+            yield self.omega_list[i], e.omega[i]
+
+    def sync_parameters(self) -> int:
+        """Re-establishes Parameter <-> packed-buffer aliasing after user code rebound ``param.data`` (the reference's threshold
+        sweep does, CYL:1219-1226): the Parameter's current values are copied into the packed storage and the Parameter is
+        pointed back at it.  Returns the number of parameters that had been detached.  Raises on a shape / device change."""
+        fixed = 0
+        for p, v in self._views():
+            if p.data_ptr() == v.data_ptr() and p.shape == v.shape:
+                continue
+            if p.numel() != v.numel() or p.device != v.device or p.dtype != v.dtype:
+                raise _lib.DesmoError(f"parameter rebound to an incompatible tensor: {tuple(p.shape)} {p.dtype} {p.device} "
+                                      f"(expected {tuple(v.shape)} float32 on {v.device})")
+            with torch.no_grad():
+                v.copy_(p.data.reshape(v.shape))
+            p.data = v
+            fixed += 1
+        return fixed
+
     # ---- reference surface -------------------------------------------------------------------------------------------
     def set_pod_modes(self, pod_modes) -> None:
         self.engine.set_pod_modes(pod_modes)
@@ -131,17 +193,26 @@ class _DesmoBase(nn.Module):
         return torch.stack([p * e.P[i, :e.n] for i, p in enumerate(self.phi_list)], dim=1)
 
     def forward(self, X=None):
-        """(recon (m, n), latent_spatial (n, r), z_values (T, m)) as CYL:576.  ``X`` is ignored, as in the reference."""
+        """(recon (m, n), latent_spatial (n, r), z_values (T, m)) as CYL:576.  ``X`` is ignored, as in the reference.
+        All three are differentiable like the reference's (recon through the fused backward kernels)."""
         e = self.engine
-        with torch.no_grad():
+        self.sync_parameters()
+        names, params = self._named_for_autograd()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            recon = _FusedRecon.apply(e, names, *params)
+        else:
             recon = e.reconstruct()
-            lat = (e.phi[:, :e.n] * e.P[:, :e.n]).t()
-            zv = e.rows[:e.T, :e.m].clone()
+        lat = self.latent_spatial()
+        if e.nF:
+            zv = e.rows[:e.T, :e.m].clone()  # series as evaluated by the last build_w (FCYL:563)
+        else:
+            zv = torch.stack(list(self.z_list), dim=0)  # CYL:550
         return recon, lat, zv
 
     def mse_loss(self, snapshot: Optional[torch.Tensor] = None) -> torch.Tensor:
         """criterion(model(snapshot)[0], snapshot) (CYL:711,722) without materialising recon; differentiable w.r.t. every
         parameter of the module (backward = the fused residual+grad kernel)."""
+        self.sync_parameters()
         if snapshot is not None:
             self.engine.set_snapshot(snapshot)
         names, params = self._named_for_autograd()

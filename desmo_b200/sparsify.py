@@ -11,9 +11,11 @@ def threshold_sweep(model, snapshot_norm2: float, thresholds=None) -> List[Tuple
     ||X - recon^T|| / ||X|| (CYL:1257) and count the surviving non-zero gates (CYL:1260-1265).
     Returns [(threshold, relative_error, n_active, mask)], restoring the gates afterwards."""
     e = model.engine
+    if hasattr(model, "sync_parameters"):
+        model.sync_parameters()
     if thresholds is None:
         thresholds = [10.0 ** (-4 + 0.5 * i) for i in range(14)]  # 10^-4 .. 10^2.5, half-decade steps (CYL:1213)
-    norms = e.term_norms()
+    norms = e.term_norms()  # the reference's semantics (raw phi_list; Fourier column quirk), see DesmoEngine.term_norms
     saved = e.gates.clone()
     out = []
     for thr in thresholds:
@@ -39,6 +41,8 @@ def greedy_removal(model, snapshot_norm2: float) -> List[Tuple[int, float, int]]
     (TURB:1227) and count the non-zero gates left (TURB:1229-1234).  One gradient-free fused pass per step on the resident
     snapshot instead of a DataLoader round trip + host numpy.  Returns [(step, relative_error, nonzero_terms)], gates restored."""
     e = model.engine
+    if hasattr(model, "sync_parameters"):
+        model.sync_parameters()
     order = removal_order(e.term_norms(), e.T, e.r)
     saved = e.gates.clone()
     out = []

@@ -86,6 +86,8 @@ class DesmoTrainer:
         """One epoch (CYL:706-778).  Returns (mse, ortho, l1, total) on scheduler epochs, else None (no host sync)."""
         if snapshot is not None:
             self.engine.set_snapshot(snapshot)
+        if self.epoch % self.sched_every == 0 and hasattr(self.model, "sync_parameters"):
+            self.model.sync_parameters()  # user code may have rebound param.data (CYL:1219-1226); cheap, only on scheduler epochs
         self._launch()
         out = None
         if self.epoch % self.sched_every == 0:
@@ -114,8 +116,10 @@ class DesmoTrainer:
     def load_state_dict(self, sd: dict) -> None:
         e = self.engine
         shp = sd["shape"]
-        if (shp["n"], shp["m"], shp["r"], shp["polyorder"], shp["nF"]) != (e.n, e.m, e.r, e.polyorder, e.nF):
-            raise ValueError(f"checkpoint shape {shp} does not match the engine")
+        if (shp["n"], shp["m"], shp["r"], shp["polyorder"], shp["nF"], shp.get("n_global", shp["n"])) != \
+                (e.n, e.m, e.r, e.polyorder, e.nF, e.n_global):
+            raise ValueError(f"checkpoint shape {shp} does not match the engine (n={e.n}, m={e.m}, r={e.r}, p={e.polyorder}, "
+                             f"nF={e.nF}, n_global={e.n_global}); re-shard with desmo_b200.checkpoint first")
         if sd.get("model") is not None and hasattr(self.model, "load_state_dict"):
             self.model.load_state_dict(sd["model"], strict=True)
         for k, v in sd["optimizer"].items():
@@ -125,6 +129,8 @@ class DesmoTrainer:
         e.P[:, :e.n].copy_(sd["pod_modes"])
         sc = sd["scheduler"]
         self.scheduler.lrs, self.scheduler.best, self.scheduler.num_bad = list(sc["lrs"]), sc["best"], sc["num_bad"]
+        self.scheduler.patience = int(sc.get("patience", self.scheduler.patience))  # the LR schedule continues as it was configured
+        self.sched_every = int(sd.get("sched_every", self.sched_every))
         self.epoch, self.beta, self.l1_lambda = int(sd["epoch"]), float(sd["beta"]), float(sd["l1_lambda"])
         e.set_hyper(self.scheduler.lrs, self.beta, self.l1_lambda)
 

@@ -93,6 +93,14 @@ int desmo_build_w(const desmo_shape* s, const float* gates, float* rows, const f
 int desmo_fused_residual_grad(const desmo_shape* s, const float* U, const float* P, const float* phi, const float* omega,
                               const float* W, float* dphi, float* red, void* workspace, void* stream);
 
+/* Backward of forward()'s reconstruction for an ARBITRARY upstream gradient (what autograd runs when the reference loop does
+ * `recon, _, _ = model(snapshot); loss = criterion(recon, snapshot); total_loss.backward()`, CYL:711,722,766): grad_recon[m][ld]
+ * = dL/drecon in the layout of U (pad columns zero).  Same kernels and outputs as desmo_fused_residual_grad with R := (n_global *
+ * m / 2) * grad_recon supplied instead of formed, so that desmo_assemble_grads / desmo_adamax_update (which apply the MSE scale
+ * 2 / (n_global * m)) yield exactly dL/d(parameter).  red's "sum of squared residuals" slot is meaningless after this call. */
+int desmo_recon_backward(const desmo_shape* s, const float* grad_recon, const float* P, const float* phi, const float* omega,
+                         const float* W, float* dphi, float* red, void* workspace, void* stream);
+
 /* Loss assembly + regulariser sub-gradients + Adamax (CYL:714-733,592-612,765-768) for every parameter.
  * `red` must hold the all-reduced buffer.  losses_out[4] = {mse, ortho, l1, total} of the step just taken
  * (computed from the pre-update parameters, as CYL:776-777 prints them). */
@@ -113,10 +121,20 @@ int desmo_assemble_grads(const desmo_shape* s, const float* red, float* dphi, co
 int desmo_reconstruct(const desmo_shape* s, const float* P, const float* phi, const float* omega, const float* W,
                       float* out, void* stream);
 
-/* Post-hoc sparsification inputs: squared column norms of G (K floats, local partial; poly_norm/nonlinear_norm
- * CYL:624-692 use |gate_j| * ||G_j|| * ||z_j||). */
+/* Post-hoc sparsification inputs: squared column norms of G (K floats, local partial -- all-reduce them across ranks).
+ * P == NULL evaluates the library on the raw phi_list, which is what the reference's sweep passes to poly_norm /
+ * nonlinear_norm (CYL:1192-1194; the functions, CYL:624-692, never multiply by POD_modes); P != NULL gives the columns of
+ * forward()'s library (phi * POD). */
 int desmo_library_colnorm2(const desmo_shape* s, const float* P, const float* phi, const float* omega, float* out_k,
                            void* stream);
+
+/* Term norms of the post-hoc sweep in closed form, K order: norms_out[j] = |gate_j| * sqrt(g2[j]) * ||z_j||  (= torch.norm(gate_j *
+ * (G_j z_j^T)), poly_norm CYL:624-647 / nonlinear_norm CYL:653-692) from the (all-reduced) g2 of desmo_library_colnorm2 and
+ * the temporal rows [K][mld] (for DESMOFourier: as evaluated by desmo_build_w).  fourier_quirk != 0 reproduces the Fourier
+ * scripts' poly_norm, which slices the (T, m) stack of series by columns (FCYL:652,659): polynomial term i is weighted by
+ * sqrt(sum_{j<T} z_j(t_i)^2).  The active mask of a threshold is norms >= threshold && gate != 0 (CYL:1228-1238,1260-1265). */
+int desmo_term_norms(const desmo_shape* s, const float* g2, const float* gates, const float* rows, int32_t fourier_quirk,
+                     double* norms_out, void* stream);
 
 /* Measurement: device time (CUDA events on the launching stream) of the dominant kernel of the last
  * desmo_fused_residual_grad call, recorded when DESMO_KERNEL_EVENTS is set in the environment.  Synchronous. */
@@ -127,7 +145,7 @@ int desmo_last_fused_kernel_ms(float* ms);
 int desmo_debug_timers(const desmo_shape* s, void* workspace, uint64_t* out_host, int32_t count);
 
 /* POD by the method of snapshots (replaces np.linalg.svd, CYL:197-205):
- *   gram    C[m][m] = U U^T  (local partial, TF32x3 tensor-core tiles)      -- all-reduce it across ranks
+ *   gram    C[m][m] = U U^T  (local partial; tcgen05 tiles with every fp32 operand split into three bf16 planes) -- all-reduce it across ranks
  *   eig     top-r eigenpairs of C (replicated, on device): sigma[r] = sqrt(lambda), V[r][m]
  *   project P[i][x] = sum_t U[t][x] V[i][t] / sigma_i, sign-normalised so that the largest-|.| entry of V_i is positive */
 int desmo_pod_gram(const desmo_shape* s, const float* U, float* C, void* workspace, void* stream);

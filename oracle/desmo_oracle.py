@@ -479,13 +479,31 @@ def pod_analysis(X: np.ndarray, r: int):
     return modes, Vt[:r, :], S, err
 
 
-def term_norms(p: DesmoParams, pod_modes: np.ndarray) -> np.ndarray:
-    """Frobenius norm of every rank-1 term, K order: ||gate_j * G_j z_j^T||_F = |gate_j| ||G_j|| ||z_j||
-    (poly_norm CYL:624-647, nonlinear_norm CYL:653-692).  DESMO variant only -- the Fourier scripts'
-    ``poly_norm`` slices the coefficient matrix differently (FCYL:652,659), see ``term_norms_fourier_quirk``."""
-    G, _ = spatial_library(p, pod_modes)
-    z = temporal_rows(p)
-    return (np.abs(p.gates) * np.linalg.norm(G.astype(np.float64), axis=0) * np.linalg.norm(z.astype(np.float64), axis=1))
+def term_norms(p: DesmoParams, pod_modes: Optional[np.ndarray] = None, physical: bool = False) -> np.ndarray:
+    """Per-term norms in K order as the reference's post-hoc sweep computes them (poly_norm CYL:624-647, nonlinear_norm
+    CYL:653-692; Fourier scripts FCYL:644-720), closed form of ``torch.norm(gate * (lib_col @ z.T))``.
+
+    Reference semantics (default), reproduced on purpose because the active mask is defined by them:
+      * the scripts pass the RAW ``model_desmo.phi_list`` (CYL:1192-1194, FCYL:1195-1197), so the library is evaluated on
+        phi alone, NOT on phi * POD_modes as in forward();
+      * DESMO: ``zs = stack(z_list, dim=1)`` is (m, T) and ``zs[:, i:i+1]`` is term i's series: norm_i = |c_i| ||L_i|| ||z_i||;
+      * DESMOFourier: ``zs = stack(..., dim=0)`` is (T, m) but is sliced the same way (FCYL:652,659), so ``zs[:, i:i+1]`` holds
+        ALL T polynomial series at time index i: norm_i = |c_i| ||L_i|| sqrt(sum_j z_j(t_i)^2).  The sin/cos/tanh norms use
+        the term's own series in both variants (FCYL:693-704).
+    ``physical=True`` gives the Frobenius norm of the term as it enters forward() (library of phi * POD, own series)."""
+    if physical:
+        G, _ = spatial_library(p, pod_modes)
+    else:
+        ones = np.ones((p.n, p.r), dtype=p.phi.dtype)
+        G, _ = spatial_library(p, ones)
+    z = temporal_rows(p).astype(np.float64)
+    zn = np.linalg.norm(z, axis=1)
+    if p.fourier and not physical:
+        T = p.T
+        if T > p.m:
+            raise ValueError("the Fourier scripts' poly_norm indexes time step i for term i: needs T <= m")
+        zn[:T] = np.sqrt(np.sum(z[:T, :T] ** 2, axis=0))  # column i of the (T, m) stack
+    return np.abs(p.gates.astype(np.float64)) * np.linalg.norm(G.astype(np.float64), axis=0) * zn
 
 
 def active_mask(norms: np.ndarray, gates: np.ndarray, threshold: float) -> np.ndarray:
@@ -512,7 +530,7 @@ def removal_order(norms: np.ndarray, T: int, r: int) -> List[int]:
 def greedy_removal(p: DesmoParams, pod_modes: np.ndarray, snapshot: np.ndarray):
     """Greedy term-removal sweep (TURB:1166-1245): for step = 0..K zero the gates of the ``step`` smallest-norm terms, evaluate
     ||X - recon^T|| / ||X|| (TURB:1227) and count the non-zero gates left (TURB:1229-1234).  Returns [(step, error, nonzero)]."""
-    order = removal_order(term_norms(p, pod_modes), p.T, p.r)
+    order = removal_order(term_norms(p), p.T, p.r)
     out = []
     for step in range(p.K + 1):
         mask = np.ones(p.K, bool)

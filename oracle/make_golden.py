@@ -39,7 +39,10 @@ TRAJ_CASES = [
     ("traj_cyl_r4p3", "cylinder", 180, 60, 4, 3, None, None, 1e-3, 1e-4, 1000, 10.0, TAME_LRS, (1, 10, 100, 1000)),
     ("traj_fcyl_r2p2", "cylinder", 180, 60, 2, 2, 6, 60.0, 1e-3, 1e-4, 1000, 10.0, TAME_LRS, (1, 10, 100, 1000)),
     ("traj_default_cyl_r4p3", "cylinder", 180, 60, 4, 3, None, None, 1e-3, 1e-4, 3, 10000.0, orc.REFERENCE_LRS, (1, 2, 3)),
+    # the headline library (r = 4, p = 2, K = 27: the tcgen05 path) on channel-like data, two time slabs and three point tiles
+    ("traj_chan_r4p2", "channel", 300, 150, 4, 2, None, None, 1e-6, 1e-4, 1000, 10.0, TAME_LRS, (1, 10, 100, 1000)),
 ]
+THRESHOLDS = [float(pow(10, -i)) for i in np.arange(4, -3, -0.5)]  # CYL:1213
 
 
 def build_inputs(kind, n, m, r, seed=0):
@@ -76,6 +79,68 @@ def grads_packed(model, params):
     else:
         out["zall"] = q.zall
     return out
+
+
+def reference_norms(model, ns, fourier):
+    """polynorms / nlnorms exactly as the scripts call them (CYL:1192-1194, FCYL:1195-1197): with the RAW phi_list."""
+    with torch.no_grad():
+        if fourier:
+            pn = ns["poly_norm"](model.c_coef, model.z_list, model.phi_list, model.period_list)
+            nl = ns["nonlinear_norm"](model.sin_coef_list, model.cos_coef_list, model.tanh_coef_list, model.zsin_list,
+                                      model.zcos_list, model.ztanh_list, model.phi_list, model.omega_list, model.trig_period_list)
+        else:
+            pn = ns["poly_norm"](model.c_coef, model.z_list, model.phi_list)
+            nl = ns["nonlinear_norm"](model.sin_coef_list, model.cos_coef_list, model.tanh_coef_list, model.zsin_list,
+                                      model.zcos_list, model.ztanh_list, model.phi_list, model.omega_list)
+    return torch.stack(pn), torch.stack(nl)
+
+
+def reference_threshold_sweep(model, ns, X, snap, fourier):
+    """The post-hoc sweep of CYL:1184-1265 / FCYL:1187-1268 run on the reference module (statement for statement; the
+    DataLoader round trip is the single full batch ``snap``).  Returns norms and, per threshold, the relative error
+    (CYL:1257), the non-zero count (CYL:1260-1265) and the surviving-gate mask in packed K order."""
+    model_desmo = model
+    original_c_coef = model_desmo.c_coef.clone()
+    original_sin_coef_list = [c.clone() for c in model_desmo.sin_coef_list]
+    original_cos_coef_list = [c.clone() for c in model_desmo.cos_coef_list]
+    original_tanh_coef_list = [c.clone() for c in model_desmo.tanh_coef_list]
+    polynorms, nlnorms = reference_norms(model_desmo, ns, fourier)
+    errs, counts, masks = [], [], []
+    for threshold in THRESHOLDS:
+        model_desmo.c_coef.data = original_c_coef.clone()
+        for i, _ in enumerate(model_desmo.sin_coef_list):
+            model_desmo.sin_coef_list[i].data = original_sin_coef_list[i].clone()
+        for i, _ in enumerate(model_desmo.cos_coef_list):
+            model_desmo.cos_coef_list[i].data = original_cos_coef_list[i].clone()
+        for i, _ in enumerate(model_desmo.tanh_coef_list):
+            model_desmo.tanh_coef_list[i].data = original_tanh_coef_list[i].clone()
+        with torch.no_grad():
+            model_desmo.c_coef.data[torch.abs(polynorms) < threshold] = 0
+            for i, sin_coef in enumerate(model_desmo.sin_coef_list):
+                sin_coef.data[torch.abs(nlnorms[i * 3]) < threshold] = 0
+            for i, cos_coef in enumerate(model_desmo.cos_coef_list):
+                cos_coef.data[torch.abs(nlnorms[i * 3 + 1]) < threshold] = 0
+            for i, tanh_coef in enumerate(model_desmo.tanh_coef_list):
+                tanh_coef.data[torch.abs(nlnorms[i * 3 + 2]) < threshold] = 0
+        model_desmo.eval()
+        with torch.no_grad():
+            recon, _, _ = model_desmo(snap)
+        errs.append(float(np.linalg.norm(X - recon.detach().numpy().T) / np.linalg.norm(X)))
+        nonzero = (torch.sum(model_desmo.c_coef != 0).item() + sum(torch.sum(c != 0).item() for c in model_desmo.sin_coef_list) +
+                   sum(torch.sum(c != 0).item() for c in model_desmo.cos_coef_list) +
+                   sum(torch.sum(c != 0).item() for c in model_desmo.tanh_coef_list))
+        counts.append(int(nonzero))
+        masks.append(np.concatenate([(model_desmo.c_coef != 0).numpy()] +
+                                    [np.array([bool(c != 0) for c in lst]) for lst in
+                                     (model_desmo.sin_coef_list, model_desmo.cos_coef_list, model_desmo.tanh_coef_list)]))
+    model_desmo.c_coef.data = original_c_coef.clone()
+    for lst, orig in ((model_desmo.sin_coef_list, original_sin_coef_list), (model_desmo.cos_coef_list, original_cos_coef_list),
+                      (model_desmo.tanh_coef_list, original_tanh_coef_list)):
+        for i, _ in enumerate(lst):
+            lst[i].data = orig[i].clone()
+    return {"sweep_poly_norms": polynorms.numpy().astype(np.float64), "sweep_nl_norms": nlnorms.numpy().astype(np.float64),
+            "sweep_thresholds": np.array(THRESHOLDS), "sweep_err": np.array(errs), "sweep_nonzero": np.array(counts),
+            "sweep_masks": np.stack(masks)}
 
 
 ANEU = "DESMO/aneurysm/DESMO_ICA_norm.py"
@@ -179,16 +244,9 @@ def main():
               "latent": lat.numpy(), "z_values": zv.numpy()}
         for k, v in g.items():
             fx["grad_" + k] = v
-        if nF is None:
-            with torch.no_grad():
-                pn = ns["poly_norm"](model.c_coef, model.z_list, [q * torch.from_numpy(modes[:, i]).float()
-                                                                  for i, q in enumerate(model.phi_list)])
-                nl = ns["nonlinear_norm"](model.sin_coef_list, model.cos_coef_list, model.tanh_coef_list, model.zsin_list,
-                                          model.zcos_list, model.ztanh_list,
-                                          [q * torch.from_numpy(modes[:, i]).float() for i, q in enumerate(model.phi_list)],
-                                          model.omega_list)
-            fx["poly_norms"] = np.array([float(v) for v in pn])
-            fx["nl_norms"] = np.array([float(v) for v in nl])  # order: sin_i, cos_i, tanh_i per mode (CYL:686-688)
+        pn, nl = reference_norms(model, ns, nF is not None)   # raw phi_list, as the scripts call them
+        fx["poly_norms"] = pn.numpy().astype(np.float64)
+        fx["nl_norms"] = nl.numpy().astype(np.float64)  # order: sin_i, cos_i, tanh_i per mode (CYL:686-688)
         np.savez_compressed(os.path.join(OUT, f"grad_{name}.npz"), **fx)
         print(name, "mse", mse.item(), "ortho", ortho.item(), "l1", l1.item())
 
@@ -197,7 +255,7 @@ def main():
         snap = torch.from_numpy(np.ascontiguousarray(X.T.astype(np.float32)))
         base = orc.init_params(n, m, p, r, omega_init=om0, nF=nF, period_init=per0 or 60.0)
         prm = orc.perturb(base, seed=43, rel=0.02)  # tiny perturbation: keeps ortho signs away from rounding noise
-        model, _ = make_model(r, p, n, m, nF, per0, modes)
+        model, ns = make_model(r, p, n, m, nF, per0, modes)
         load_packed(model, prm)
         opt = ref.reference_optimizer(model, nF is not None)
         for grp, lr in zip(opt.param_groups, lrs):
@@ -224,6 +282,8 @@ def main():
                                       omega_init=om0, lrs=list(lrs), marks=list(marks))),
               "hist": np.array(hist), "final_lrs": np.array([g["lr"] for g in opt.param_groups])}
         fx.update(snaps)
+        if steps >= 1000:  # post-hoc sweep on the trained reference module: norms, masks, errors (CYL:1184-1265)
+            fx.update(reference_threshold_sweep(model, ns, X, snap, nF is not None))
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **fx)
         print(name, "first", hist[0], "last", hist[-1], "lrs", fx["final_lrs"])
 

@@ -59,12 +59,14 @@ def test_step_loss_and_grads_match_reference_golden(name, path):
     _check_grads(e, out, meta["beta"], meta["l1_lambda"])
     recon = e.reconstruct().cpu().numpy()
     assert rel(recon[::7, ::5], fx["recon_sample"]) < 1e-5
-    if "poly_norms" in fx.files:
-        norms = e.term_norms().cpu().numpy()
-        T, r = prm.T, prm.r
-        nl = fx["nl_norms"].reshape(r, 3)
-        ref_norms = np.concatenate([fx["poly_norms"], nl[:, 0], nl[:, 1], nl[:, 2]])
-        assert rel(norms, ref_norms) < 1e-5
+    # post-hoc term norms as the scripts call poly_norm / nonlinear_norm (raw phi_list; Fourier column quirk, FCYL:652,659)
+    assert rel(e.term_norms().cpu().numpy(), _packed_norms(fx["poly_norms"], fx["nl_norms"], prm.r)) < 5e-6
+
+
+def _packed_norms(poly, nl, r):
+    """Reference order (poly..., then sin_i, cos_i, tanh_i per mode, CYL:686-688) -> packed K order [poly | sin | cos | tanh]."""
+    nl = np.asarray(nl).reshape(r, 3)
+    return np.concatenate([np.asarray(poly), nl[:, 0], nl[:, 1], nl[:, 2]])
 
 
 CASES = [  # (kind, n, m, r, p, nF) -- ragged sizes, single tile, multi tile, chunked time axis (K*m too big for one CTA)
@@ -77,6 +79,8 @@ CASES = [  # (kind, n, m, r, p, nF) -- ragged sizes, single tile, multi tile, ch
     ("cylinder", 300, 40, 3, 3, 3),         # Fourier, odd sizes
     ("cylinder", 3961, 1001, 8, 2, None),   # C1 with BASELINE's "8 modes": K = 69 -> Kp = 80 (FFMA path)
     ("cylinder", 700, 90, 8, 2, 4),         # 8 modes, Fourier temporal library
+    ("channel", 16384, 1000, 4, 2, None),   # C3 script shape (TURB): 128 point tiles x 8 time slabs on the tcgen05 path
+    ("aneurysm", 27000, 1000, 4, 2, None),  # C4 script shape (ANEU): ragged last tile, ragged last slab
 ]
 
 
@@ -95,7 +99,7 @@ def test_step_loss_and_grads_match_oracle(case, path):
 
 
 @pytest.mark.parametrize("path", PATHS)
-@pytest.mark.parametrize("name", ["traj_cyl_r4p3", "traj_fcyl_r2p2", "traj_default_cyl_r4p3"])
+@pytest.mark.parametrize("name", ["traj_cyl_r4p3", "traj_fcyl_r2p2", "traj_default_cyl_r4p3", "traj_chan_r4p2"])
 def test_training_trajectory_matches_reference_golden(name, path):
     """1000 fused steps (device Adamax + host plateau scheduler) vs the reference's torch.optim.Adamax trajectory."""
     from desmo_b200 import DesmoTrainer
@@ -150,7 +154,10 @@ def test_module_surface_and_state_dict_roundtrip():
     model = DESMO(prm.n, prm.m, 3, 4, 10000, pod_modes=modes, device=torch.device("cuda:0"), path=1)
     ck = facts["checkpoints"]["DESMO/cylinder_flow/DESMO_r4_final_2025-01-25_17-08-31.pt"]
     assert list(model.state_dict().keys()) == ck["keys"]
-    assert [list(v.shape) for v in model.state_dict().values()][0] == ck["shapes"][0]
+    shapes = [list(v.shape) for v in model.state_dict().values()]
+    n_ck = ck["shapes"][ck["keys"].index("phi_list.0")][0]  # the shipped checkpoint's mesh size differs from this test's
+    m_ck = ck["shapes"][ck["keys"].index("z_list.0")][0]
+    assert [[prm.n if d == n_ck else prm.m if d == m_ck else d for d in sh] for sh in ck["shapes"]] == shapes
     assert sum(p.numel() for p in model.parameters()) == orc.init_params(prm.n, prm.m, 3, 4).num_parameters()
     sd = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in orc.to_state_dict(prm).items()}
     model.load_state_dict(sd, strict=True)
@@ -172,43 +179,196 @@ def test_module_surface_and_state_dict_roundtrip():
     assert rel(torch.stack([p.grad for p in model.omega_list]).cpu().numpy(), o.grads["omega"]) < 5e-5
     recon, lat2, zv = model(snap_t)
     r_o, l_o, z_o = orc.forward(prm, modes)
-    assert recon.shape == (prm.m, prm.n) and rel(recon.cpu().numpy(), r_o) < 1e-5 and rel(lat2.cpu().numpy(), l_o) < 1e-6
-    assert rel(zv.cpu().numpy(), z_o) == 0.0
+    assert recon.grad_fn is not None and lat2.requires_grad and zv.requires_grad  # differentiable like the reference's 3-tuple
+    assert recon.shape == (prm.m, prm.n) and rel(recon.detach().cpu().numpy(), r_o) < 1e-5 and rel(lat2.detach().cpu().numpy(), l_o) < 1e-6
+    assert rel(zv.detach().cpu().numpy(), z_o) == 0.0
     fm = DESMOFourier(150, 64, 2, 2, 10000, 10, period_init=60.0, device=torch.device("cuda:0"), path=1)
     ckf = facts["checkpoints"]["DESMO_Fourier/cylinder_flow/DESMOCF_r2_final_2025-02-11_16-45-07.pt"]
     assert list(fm.state_dict().keys()) == ckf["keys"]
-    assert [list(v.shape) for v in fm.state_dict().values()][1:] == ckf["shapes"][1:] or True
+    n_ckf = ckf["shapes"][ckf["keys"].index("phi_list.0")][0]
+    assert [[150 if d == n_ckf else d for d in sh] for sh in ckf["shapes"]] == [list(v.shape) for v in fm.state_dict().values()]
     assert sum(p.numel() for p in fm.parameters()) == orc.init_params(150, 64, 2, 2, nF=10).num_parameters()
 
 
-def test_active_mask_matches_oracle_after_training():
-    """Post-hoc sparsification (CYL:1184-1270): identical active-term mask and matching relative errors."""
+THRESHOLDS = [10.0 ** (-4 + 0.5 * i) for i in range(14)]  # CYL:1213
+
+
+def _load_final(e, fx, meta, prm, modes, snap):
+    q = prm.copy()
+    for k in ("gates", "phi", "omega", "zall", "coefs", "periods"):
+        if getattr(q, k) is not None:
+            setattr(q, k, fx[f"step{meta['steps']}_{k}"].copy())
+    load_engine(e, q, modes, snap)
+    return q
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("name", ["traj_chan_r4p2", "traj_fcyl_r2p2", "traj_cyl_r4p3"])
+def test_threshold_sweep_matches_reference_golden(name, path):
+    """Post-hoc sparsification against the REFERENCE's own sweep (CYL:1184-1265 run on the reference module by
+    oracle/make_golden.py after its 1000-step run), on the same trained parameters: term norms, the exactly identical active mask
+    at every one of the 14 thresholds (no skip window), non-zero counts, relative errors.  Covers the Fourier scripts' norm."""
+    from desmo_b200 import DESMO, DESMOFourier
+    from desmo_b200.sparsify import threshold_sweep
+
+    fx, meta, modes, snap, prm = golden_case(name)
+    if path == 2 and prm.K > 32:
+        pytest.skip("K > 32")
+    dev = torch.device("cuda:0")
+    if prm.fourier:
+        model = DESMOFourier(prm.n, prm.m, prm.polyorder, prm.r, 10.0, prm.nF, period_init=meta["period_init"], pod_modes=modes, device=dev, path=path)
+    else:
+        model = DESMO(prm.n, prm.m, prm.polyorder, prm.r, 10.0, pod_modes=modes, device=dev, path=path)
+    _load_final(model.engine, fx, meta, prm, modes, snap)
+    want_norms = _packed_norms(fx["sweep_poly_norms"], fx["sweep_nl_norms"], prm.r)
+    assert rel(model.engine.term_norms().cpu().numpy(), want_norms) < 5e-6
+    sweep = threshold_sweep(model, float((snap.astype(np.float64) ** 2).sum()), list(fx["sweep_thresholds"]))
+    for i, (thr, err, n_active, mask) in enumerate(sweep):
+        assert np.array_equal(mask.cpu().numpy(), fx["sweep_masks"][i]), thr
+        assert n_active == int(fx["sweep_nonzero"][i])
+        assert abs(err - fx["sweep_err"][i]) < 2e-5, (thr, err, fx["sweep_err"][i])
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_active_mask_after_device_training_matches_reference(path):
+    """1000 fused train steps on the device from the golden's start, then the sweep: the active mask equals the one the reference
+    obtains after ITS 1000 steps.  The two trajectories agree to 1e-3 (north_star), so a threshold is only decidable if no
+    reference norm lies within that distance of it; the fixture has one such near-tie (norm 9.979 vs threshold 10: 2.1e-3), kept."""
     from desmo_b200 import DESMO, DesmoTrainer
     from desmo_b200.sparsify import threshold_sweep
 
-    _, modes, snap, prm = make_case("cylinder", 500, 80, 4, 2, omega_init=10.0, perturb_rel=0.02)
-    lrs = (1e-2, 1e-3, 1e-2, 1e-2)
-    ref = prm.copy()
-    orc.train(ref, modes, snap, 200, 1e-3, 1e-4, lrs=lrs + (1e-2,))
-    model = DESMO(prm.n, prm.m, 2, 4, 10.0, pod_modes=modes, device=torch.device("cuda:0"), path=1)
+    fx, meta, modes, snap, prm = golden_case("traj_chan_r4p2")
+    model = DESMO(prm.n, prm.m, prm.polyorder, prm.r, 10.0, pod_modes=modes, device=torch.device("cuda:0"), path=path)
     load_engine(model.engine, prm, modes, snap)
-    tr = DesmoTrainer(model, lrs=lrs, beta=1e-3, l1_lambda=1e-4)
-    for _ in range(200):
+    tr = DesmoTrainer(model, lrs=meta["lrs"], beta=meta["beta"], l1_lambda=meta["l1_lambda"], patience=meta["patience"],
+                      sched_every=meta["sched_every"])
+    for _ in range(meta["steps"]):
         tr.step()
-    norms_ref = orc.term_norms(ref, modes)
+    want_norms = _packed_norms(fx["sweep_poly_norms"], fx["sweep_nl_norms"], prm.r)
     norms = model.engine.term_norms().cpu().numpy()
-    assert rel(norms, norms_ref) < 1e-3
-    x2 = float((snap.astype(np.float64) ** 2).sum())
-    thresholds = [10.0 ** (-4 + 0.5 * i) for i in range(14)]
-    # thresholds that fall within 1e-3 relative of a term norm are numerically undecidable on either side: skip those
-    sweep = threshold_sweep(model, x2, thresholds)
-    for thr, err, n_active, mask in sweep:
-        if np.min(np.abs(norms_ref - thr) / thr) < 2e-3:
-            continue
-        want = orc.active_mask(norms_ref, ref.gates, thr)
-        assert np.array_equal(mask.cpu().numpy(), want), thr
-        assert n_active == int(want.sum())
-        assert abs(err - orc.relative_error(ref, modes, snap, want)) < 2e-3
+    assert rel(norms, want_norms) < 1e-3
+    # Decidability.  north_star's trajectory tolerance is 1e-3 relative per parameter GROUP (Frobenius), i.e. a gate may differ by
+    # delta = 1e-3 * ||gates||_2 in absolute terms; a gate that the L1 term has driven to ~1e-5 is pure noise at that tolerance.
+    # Term j at threshold t is decidable iff the reference norm |g_j| a_j (a_j = ||L_j|| ||z_j||) is farther from t than delta * a_j.
+    g_ref = fx[f"step{meta['steps']}_gates"].astype(np.float64)
+    a = want_norms / np.abs(g_ref)
+    delta = 1e-3 * np.linalg.norm(g_ref)
+    sweep = threshold_sweep(model, float((snap.astype(np.float64) ** 2).sum()), list(fx["sweep_thresholds"]))
+    undecidable = 0
+    for i, (thr, err, n_active, mask) in enumerate(sweep):
+        dec = np.abs(want_norms - thr) > delta * a + 1e-3 * thr
+        undecidable += int((~dec).sum())
+        got = mask.cpu().numpy()
+        assert np.array_equal(got[dec], fx["sweep_masks"][i][dec]), thr
+        if dec.all():
+            assert n_active == int(fx["sweep_nonzero"][i])
+            assert abs(err - fx["sweep_err"][i]) < 2e-3
+    assert undecidable <= 12, undecidable  # of 14 x 27 (term, threshold) pairs (10 measured): the one gate near zero, below its own noise band
+
+
+def test_reference_sweep_code_runs_unmodified_on_the_module():
+    """The literal thresholding statements of CYL:1219-1238 (which REBIND ``param.data`` to clones) against the drop-in module:
+    the module re-aliases the detached parameters before its next launch, so every threshold sees its own gates."""
+    from desmo_b200 import DESMO
+
+    fx, meta, modes, snap, prm = golden_case("traj_chan_r4p2")
+    model_desmo = DESMO(prm.n, prm.m, prm.polyorder, prm.r, 10.0, pod_modes=modes, device=torch.device("cuda:0"), path=0)
+    q = _load_final(model_desmo.engine, fx, meta, prm, modes, snap)
+    norms = model_desmo.engine.term_norms().float()
+    T, r = q.T, q.r
+    polynorms = norms[:T]
+    nlnorms = torch.stack([norms[T + b * r + i] for i in range(r) for b in range(3)])  # sin_i, cos_i, tanh_i per mode (CYL:686-688)
+    snapshot = torch.from_numpy(snap).cuda()
+    X = snap.T.astype(np.float64)
+    original_c_coef = model_desmo.c_coef.clone()
+    original_sin_coef_list = [sin_coef.clone() for sin_coef in model_desmo.sin_coef_list]
+    original_cos_coef_list = [cos_coef.clone() for cos_coef in model_desmo.cos_coef_list]
+    original_tanh_coef_list = [tanh_coef.clone() for tanh_coef in model_desmo.tanh_coef_list]
+    errs, counts = [], []
+    for threshold in fx["sweep_thresholds"]:
+        # ---- CYL:1219-1238, verbatim ----
+        model_desmo.c_coef.data = original_c_coef.clone()
+        for i, sin_coef in enumerate(model_desmo.sin_coef_list):
+            model_desmo.sin_coef_list[i].data = original_sin_coef_list[i].clone()
+        for i, cos_coef in enumerate(model_desmo.cos_coef_list):
+            model_desmo.cos_coef_list[i].data = original_cos_coef_list[i].clone()
+        for i, tanh_coef in enumerate(model_desmo.tanh_coef_list):
+            model_desmo.tanh_coef_list[i].data = original_tanh_coef_list[i].clone()
+        with torch.no_grad():
+            model_desmo.c_coef.data[torch.abs(polynorms) < threshold] = 0
+            for i, sin_coef in enumerate(model_desmo.sin_coef_list):
+                sin_coef.data[torch.abs(nlnorms[i * 3]) < threshold] = 0
+            for i, cos_coef in enumerate(model_desmo.cos_coef_list):
+                cos_coef.data[torch.abs(nlnorms[i * 3 + 1]) < threshold] = 0
+            for i, tanh_coef in enumerate(model_desmo.tanh_coef_list):
+                tanh_coef.data[torch.abs(nlnorms[i * 3 + 2]) < threshold] = 0
+        model_desmo.eval()
+        with torch.no_grad():
+            recon_combined, latent_spatial, latent_temporal = model_desmo(snapshot)
+        errs.append(np.linalg.norm(X - recon_combined.detach().cpu().numpy().T.astype(np.float64)) / np.linalg.norm(X))
+        counts.append(torch.sum(model_desmo.c_coef != 0).item() + sum(torch.sum(c != 0).item() for lst in
+                      (model_desmo.sin_coef_list, model_desmo.cos_coef_list, model_desmo.tanh_coef_list) for c in lst))
+    assert counts == [int(v) for v in fx["sweep_nonzero"]]
+    assert np.allclose(errs, fx["sweep_err"], atol=2e-5)
+    assert len(set(counts)) >= 4
+    # the last forward() re-aliased what the thresholding statements had detached
+    assert model_desmo.sync_parameters() == 0 and model_desmo.c_coef.data_ptr() == model_desmo.engine.gates.data_ptr()
+    model_desmo.c_coef.data = original_c_coef.clone()  # detach once more: the values travel back into the packed buffer
+    assert model_desmo.c_coef.data_ptr() != model_desmo.engine.gates.data_ptr()
+    assert model_desmo.sync_parameters() == 1 and torch.equal(model_desmo.engine.gates[:T], original_c_coef)
+
+
+def test_reference_training_loop_runs_unmodified_on_the_module():
+    """The loop body of CYL:711-768 verbatim -- forward 3-tuple, ortho from latent_spatial, nn.MSELoss(recon, snapshot), L1,
+    total_loss.backward(), torch.optim.Adamax step with the script's four param groups (CYL:592-612) -- on the drop-in module:
+    recon carries a grad_fn whose backward is desmo_recon_backward.  Gradients of step 1 and the 5-step trajectory vs the oracle."""
+    from desmo_b200 import DESMO
+
+    for path in (1, 2):
+        _, modes, snap, prm = make_case("channel", 300, 150, 4, 2, omega_init=10.0, perturb_rel=0.05)
+        device = torch.device("cuda:0")
+        model_desmo = DESMO(prm.n, prm.m, prm.polyorder, prm.r, 10.0, pod_modes=modes, device=device, path=path)
+        load_engine(model_desmo.engine, prm, modes, snap)
+        optimizer = torch.optim.Adamax([
+            {'params': [model_desmo.c_coef] + list(model_desmo.sin_coef_list) + list(model_desmo.cos_coef_list) + list(model_desmo.tanh_coef_list), 'lr': 1e-2},
+            {'params': model_desmo.phi_list, 'lr': 1e-3},
+            {'params': list(model_desmo.z_list) + list(model_desmo.zsin_list) + list(model_desmo.zcos_list) + list(model_desmo.ztanh_list), 'lr': 1e-2},
+            {'params': model_desmo.omega_list, 'lr': 1e-2}], weight_decay=0)
+        criterion = torch.nn.MSELoss()
+        beta, l1_lambda = 1e-3, 1e-4
+        snapshot = torch.from_numpy(snap).to(device)
+        ref = prm.copy()
+        opt = orc.Adamax(ref, (1e-2, 1e-3, 1e-2, 1e-2, 1e-2))
+        for epoch in range(5):
+            recon, latent_spatial, latent_temporal = model_desmo(snapshot)
+            ortho_loss_spatial = 0
+            for i in range(latent_spatial.size(1)):
+                for j in range(i + 1, latent_spatial.size(1)):
+                    ortho_loss_spatial += torch.norm(latent_spatial[:, i] @ latent_spatial[:, j].T, p='fro')
+            loss = criterion(recon, snapshot)
+            l1_loss = torch.norm(model_desmo.c_coef, p=1)
+            for sin_coef in model_desmo.sin_coef_list:
+                l1_loss = l1_loss + torch.norm(sin_coef, p=1)
+            for cos_coef in model_desmo.cos_coef_list:
+                l1_loss = l1_loss + torch.norm(cos_coef, p=1)
+            for tanh_coef in model_desmo.tanh_coef_list:
+                l1_loss = l1_loss + torch.norm(tanh_coef, p=1)
+            total_loss = loss + beta * ortho_loss_spatial + l1_lambda * l1_loss
+            optimizer.zero_grad()
+            total_loss.backward()
+            o = orc.loss_and_grads(ref, modes, snap, beta, l1_lambda)
+            if epoch == 0:
+                assert abs(total_loss.item() - o.total) < 1e-5 * abs(o.total)
+                assert rel(model_desmo.c_coef.grad.cpu().numpy(), o.grads["gates"][:prm.T]) < 1e-5
+                assert rel(torch.stack([p.grad for p in model_desmo.z_list]).cpu().numpy(), o.grads["zall"][:prm.T]) < 1e-5
+                assert rel(torch.stack([p.grad for p in model_desmo.ztanh_list]).cpu().numpy(), o.grads["zall"][prm.T + 2 * prm.r:]) < 1e-5
+                assert rel(torch.stack([p.grad for p in model_desmo.phi_list]).cpu().numpy(), o.grads["phi"]) < 5e-5
+                assert rel(torch.stack([p.grad for p in model_desmo.omega_list]).cpu().numpy(), o.grads["omega"]) < 5e-5
+            optimizer.step()
+            opt.step(ref, o.grads)
+        got = engine_params(model_desmo.engine)  # torch's optimizer updated the packed buffers through the aliased Parameters
+        for k, v in got.items():
+            assert rel(v, getattr(ref, k)) < 1e-4, (path, k, rel(v, getattr(ref, k)))
 
 
 def test_point_sharding_is_exact_decomposition():
@@ -253,7 +413,8 @@ def test_pod_by_method_of_snapshots_matches_svd(path):
     assert np.allclose(P @ P.T, np.eye(4), atol=1e-4)
 
 
-def test_headline_size_properties():
+@pytest.mark.parametrize("path", PATHS)
+def test_headline_size_properties(path):
     """At an HBM-sized slab (2^18 points x 1000 snapshots, K=27): size-independent checks.
     (1) W = 0  =>  loss = ||U||^2 and E = -G^T U (checksum of the streaming path);
     (2) U := G W  =>  residual ~ 0, gradients ~ 0 (encode -> decode round trip);
@@ -262,7 +423,7 @@ def test_headline_size_properties():
 
     n, m, r, p = 1 << 18, 1000, 4, 2
     dev = torch.device("cuda:0")
-    e = DesmoEngine(n, m, p, r, omega_init=10.0, device=dev, path=1)
+    e = DesmoEngine(n, m, p, r, omega_init=10.0, device=dev, path=path)
     g = torch.Generator(device=dev).manual_seed(0)
     e.P[:, :n] = torch.randn(r, n, device=dev, generator=g) / n ** 0.5
     e.rows[:, :m] = torch.randn(e.K, m, device=dev, generator=g)
@@ -291,9 +452,12 @@ def test_headline_size_properties():
 
 
 def test_registered_torch_custom_ops_match_engine():
-    """The same step through torch.ops.desmo_b200.* (custom-op registration of the C ABI)."""
+    """The same step, term norms and POD init through torch.ops.desmo_b200.* (one registered op per C-ABI entry point)."""
     import desmo_b200.ops as ops
 
+    registered = {n for n in dir(torch.ops.desmo_b200) if not n.startswith("_")}
+    assert {"build_w", "fused_residual_grad", "recon_backward", "adamax_update", "assemble_grads", "reconstruct", "library_colnorm2",
+            "term_norms", "pod_gram", "pod_eig", "pod_project", "preprocess"} <= registered
     _, modes, snap, prm = make_case("aneurysm", 1000, 100, 4, 2, omega_init=10.0)
     a, b = _engine(prm, modes, snap, 0), _engine(prm, modes, snap, 0)
     for e in (a, b):
@@ -304,6 +468,15 @@ def test_registered_torch_custom_ops_match_engine():
     torch.cuda.synchronize()
     for k, v in engine_params(a).items():
         assert np.array_equal(v, engine_params(b)[k]), k
+    assert rel(ops.engine_term_norms_via_ops(b).cpu().numpy(), a.term_norms().cpu().numpy()) < 1e-6  # colnorm2 sums with float atomics
+    assert int(b.step_dev.item()) == 3
+    sa = a.pod_from_snapshot()
+    sb = ops.engine_pod_via_ops(b)
+    assert torch.equal(sa, sb) and torch.equal(a.P, b.P)
+    out = torch.empty(b.m, b.ld, device=b.device)
+    torch.ops.desmo_b200.reconstruct(b.P, b.phi, b.omega, b.W, out, *ops._shape_args(b))
+    a.build_w(False)
+    assert torch.equal(out[:, :b.n], a.reconstruct())
     with pytest.raises(Exception):
         torch.ops.desmo_b200.fused_residual_grad(a.U.cpu(), a.P.cpu(), a.phi.cpu(), a.omega.cpu(), a.W.cpu(), a.dphi.cpu(), a.red.cpu(),
                                                  a.workspace.cpu(), a.n, a.n, a.m, a.r, a.polyorder, 0, 0)
@@ -451,7 +624,7 @@ def test_greedy_removal_sweep_matches_oracle(path):
     model = DESMO(prm.n, prm.m, 2, 4, 10.0, pod_modes=modes, device=torch.device("cuda:0"), path=path)
     load_engine(model.engine, prm, modes, snap)
     want = orc.greedy_removal(prm, modes, snap)
-    norms_ref = orc.term_norms(prm, modes)
+    norms_ref = orc.term_norms(prm)
     assert removal_order(model.engine.term_norms(), prm.T, prm.r) == orc.removal_order(norms_ref, prm.T, prm.r)
     got = greedy_removal(model, float((snap.astype(np.float64) ** 2).sum()))
     assert len(got) == prm.K + 1 and [g[0] for g in got] == list(range(prm.K + 1))

@@ -97,16 +97,43 @@ def test_loss_and_grads_match_reference_autograd(path):
     o64 = orc.loss_and_grads(p64, modes, snap.astype(np.float64), meta["beta"], meta["l1_lambda"])
     for k, g in o64.grads.items():
         assert rel(g, fx["grad_" + k]) < 2e-4, (k, rel(g, fx["grad_" + k]))
-    if "poly_norms" in fx.files:
-        norms = orc.term_norms(prm, modes)
-        T, r = prm.T, prm.r
-        assert rel(norms[:T], fx["poly_norms"]) < 1e-5
-        nl = fx["nl_norms"].reshape(r, 3)  # per mode: sin, cos, tanh (CYL:686-688)
-        assert rel(norms[T:T + r], nl[:, 0]) < 1e-5 and rel(norms[T + r:T + 2 * r], nl[:, 1]) < 1e-5
-        assert rel(norms[T + 2 * r:], nl[:, 2]) < 1e-5
+    # post-hoc term norms exactly as the scripts call poly_norm / nonlinear_norm: raw phi_list (CYL:1192-1194), and in the
+    # Fourier variant the column slicing of the (T, m) stack (FCYL:652,659)
+    norms = orc.term_norms(prm)
+    assert rel(norms, packed_norms(fx["poly_norms"], fx["nl_norms"], prm.r)) < 2e-6
 
 
-@pytest.mark.parametrize("name", ["traj_cyl_r4p3", "traj_fcyl_r2p2", "traj_default_cyl_r4p3"])
+def packed_norms(poly, nl, r):
+    """Reference order (poly..., then sin_i, cos_i, tanh_i per mode, CYL:686-688) -> packed K order [poly | sin | cos | tanh]."""
+    nl = np.asarray(nl).reshape(r, 3)
+    return np.concatenate([np.asarray(poly), nl[:, 0], nl[:, 1], nl[:, 2]])
+
+
+@pytest.mark.parametrize("name", ["traj_chan_r4p2", "traj_cyl_r4p3", "traj_fcyl_r2p2"])
+def test_threshold_sweep_matches_reference(golden_dir, name):
+    """The reference's post-hoc sweep (CYL:1184-1265, run by oracle/make_golden.py on the reference module after its 1000-step
+    run) vs the oracle's restatement on the same trained parameters: norms, the EXACT active mask at every threshold, non-zero
+    counts and relative errors."""
+    fx, meta, modes, snap, prm = load_case(os.path.join(golden_dir, name + ".npz"))
+    for k in ("gates", "phi", "omega", "zall", "coefs", "periods"):
+        if getattr(prm, k) is not None:
+            setattr(prm, k, fx[f"step{meta['steps']}_{k}"].copy())
+    want_norms = packed_norms(fx["sweep_poly_norms"], fx["sweep_nl_norms"], prm.r)
+    norms = orc.term_norms(prm)
+    assert rel(norms, want_norms) < 2e-6
+    # no threshold of the sweep sits within fp32 rounding of a norm, so the mask is decidable
+    assert min(np.min(np.abs(want_norms - t) / t) for t in fx["sweep_thresholds"]) > 1e-4
+    n_distinct = set()
+    for i, thr in enumerate(fx["sweep_thresholds"]):
+        mask = orc.active_mask(norms, prm.gates, thr)
+        assert np.array_equal(mask, fx["sweep_masks"][i]), thr
+        assert int(mask.sum()) == int(fx["sweep_nonzero"][i])
+        assert abs(orc.relative_error(prm, modes, snap, mask) - fx["sweep_err"][i]) < 1e-5
+        n_distinct.add(int(mask.sum()))
+    assert len(n_distinct) >= 4  # the sweep actually prunes
+
+
+@pytest.mark.parametrize("name", ["traj_cyl_r4p3", "traj_fcyl_r2p2", "traj_default_cyl_r4p3", "traj_chan_r4p2"])
 def test_training_trajectory_matches_reference(golden_dir, name):
     """1000-step trajectories within 1e-3 relative (north_star) on the non-chaotic setting; the shipped
     omega_init=1e4 / lr=1e3 setting is chaotic (error x10 per step, see oracle/make_golden.py) and is pinned
@@ -176,7 +203,7 @@ def test_greedy_removal_sweep_properties():
 
     _, modes, snap, prm = make_case("channel", 120, 30, 3, 2, omega_init=10.0, perturb_rel=0.3)
     prm.gates[[2, 5]] = 0.0  # two zero-norm terms: the stable sort keeps the reference's list order (poly 2 before poly 5)
-    norms = orc.term_norms(prm, modes)
+    norms = orc.term_norms(prm)
     order = orc.removal_order(norms, prm.T, prm.r)
     assert order[:2] == [2, 5] and sorted(order) == list(range(prm.K))
     assert all(norms[a] <= norms[b] for a, b in zip(order, order[1:]))

@@ -22,7 +22,8 @@ t = out[:148 * 32].reshape(148, 32).astype(np.float64)
 nst = n / 128 / 148 * 8
 names = ["mma:wait W_FULL", "mma:wait REC_EMPTY", "mma:wait G_FULL", "mma:wait R_FULL", "mma:wait D_EMPTY", "", "", "",
          "epi:wait REC_FULL", "epi:phase A", "epi:wait R_EMPTY", "epi:after R_FULL (U tail loads / next library)", "epi:  R_s stores", "epi:wait G_EMPTY", "epi:G compute+store", "epi:  fence + arrive R_FULL", "epi:total",
-         "", "", "", "prod0:wait U_EMPTY", "prod0:total", "prod1:wait U_EMPTY", "prod1:total"]
+         "", "", "", "prod0:wait U_EMPTY", "prod0:total", "prod1:wait U_EMPTY", "prod1:total",
+         "epi:library phi/P loads", "epi:library terms"]
 for i, nm in enumerate(names):
     if nm:
         print(f"{nm:48s} mean {t[:, i].mean() / nst:9.0f} cycles/slab-tile   (min {t[:, i].min() / nst:8.0f}, max {t[:, i].max() / nst:8.0f})")
