@@ -3,9 +3,9 @@
 // each GEMM is accurate to ~2^-24 relative, i.e. fp32-class, at the cost of 6 bf16 MMAs = 3 TF32-equivalents).
 //
 // One persistent CTA per SM; a CTA owns tiles of 128 mesh points and walks all snapshots in slabs of 128:
-//   G1  Rec[p x t]    = G[p x lib] W[lib x t]           -> TMEM cols [0,128)                      (CYL:548,565-572)
-//   epi r = Rec - U   (U read once from HBM: 24 of a quarter's 32 snapshots through a private TMA ring, 8 by prefetching loads;
-//       R never leaves the SM) (CYL:722); sum r^2;
+//   G1  Rec[p x t]    = G[p x lib] W[lib x t]           -> TMEM cols [0,128)   (A = G planes resident in TMEM)   (CYL:548,565-572)
+//   epi r = Rec - U   (U read once from HBM through per-quarter TMA stages: U_STAGES boxes of U_ROWS snapshots x 128 points, any
+//       remaining snapshots of the quarter by register-prefetched loads; R never leaves the SM) (CYL:722); sum r^2;
 //       r -> NPR (= 2) bf16 planes (formed in registers before R_s is free), then R_s[p rows][t contiguous] in shared memory
 //       (128B-swizzled: K-major operand of G3 AND MN-major operand of G4)
 //   G3  D[p x lib]   += R[p x t] W^T[t x lib]           -> TMEM cols [128,128+32*NPR): N-stacked blocks, accumulated over the slabs
@@ -59,13 +59,16 @@ constexpr uint32_t G_OFF = W_OFF + 2 * W_SLAB;
 // Private rings matter: mbarrier parity waits are only sound if a waiter is never two phases away from the barrier, which a
 // ring shared by independently progressing consumer groups cannot guarantee.
 constexpr uint32_t U_OFF = G_OFF + 3 * G_PLANE;
+// One [32 snapshots][128 points] box (16 KB) per quarter and slab-tile: a single TMA instruction, a single FULL / EMPTY hand-over and
+// no register-prefetched tail.  Measured equal to or ~1 % faster than three 8-row stages + 8 tail loads (profiles/README.md), with 40
+// fewer instructions per thread and slab.
 #ifndef DESMO_U_ROWS
-#define DESMO_U_ROWS 8
+#define DESMO_U_ROWS 32
 #endif
 constexpr int U_ROWS = DESMO_U_ROWS;  // snapshots per TMA stage
 constexpr uint32_t U_STAGE = U_ROWS * BP * 4;          // 4096 (must be a multiple of 128 B, the TMA destination alignment)
 #ifndef DESMO_U_STAGES
-#define DESMO_U_STAGES 3
+#define DESMO_U_STAGES 1
 #endif
 constexpr int U_STAGES = DESMO_U_STAGES;               // per quarter
 constexpr int U_TAIL = QT - U_STAGES * U_ROWS;         // snapshots of a quarter fetched by the epilogue threads themselves (registers)
@@ -81,6 +84,14 @@ constexpr uint32_t SMEM_BYTES = RED_OFF + 4 * kScal * 8 + 1024;  // + alignment 
 static_assert(SMEM_BYTES + 1024 <= 232448, "dynamic + static shared memory must fit the 227 KB of an sm_100 CTA");
 static_assert(U_TAIL >= 0 && U_STAGE % 128 == 0, "U stage shape");
 constexpr uint32_t TMEM_REC = 0, TMEM_D = 128, TMEM_E = 256;  // D: NPR column blocks of 32 (N-stacked B planes), summed in the epilogue
+// G1's A operand (the three bf16 planes of the library tile, [point = lane][lib pair = column], 16 columns per plane) can live in
+// TMEM: an SS-mode MMA re-reads its 4 KB A tile from shared memory for every instruction, and shared-memory bandwidth is what
+// binds this kernel (ncu: tensor-core operand reads + LSU ~ 96 % of the data pipe).  Needs NPR == 2 (D then ends at column 192).
+#ifndef DESMO_G1_TMEM
+#define DESMO_G1_TMEM 1
+#endif
+constexpr bool G1_TMEM = DESMO_G1_TMEM && NPR == 2;
+constexpr uint32_t TMEM_G = 192;
 }  // namespace tc
 
 struct TcArgs {
@@ -185,6 +196,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// A operand in tensor memory (128 lanes = rows, 8 columns = 16 bf16 along K), B from shared memory
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 
 // x = b1 + b2 + b3 (bf16 each, round-to-nearest): packs two consecutive elements (lo = first) per 32-bit word
 // (the conversions are `volatile` so that the compiler cannot sink them below the mbarrier wait that follows them in the epilogue)
@@ -272,10 +294,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             }
         }
     } else if (warp == 3 || warp == 2) {
-        // ================= TMA producers: U chunks [8 snapshots][128 points]; each thread feeds the private rings of two quarters ==========
-        // A ring holds the first 24 of a quarter's 32 snapshots (3 stages of 8 = exactly one slab-tile), so the three boxes of the
-        // NEXT slab-tile are requested as soon as the current ones are consumed; the last 8 snapshots are fetched by the epilogue
-        // threads themselves one slab ahead (registers).  (Stages of 9 rows also fit the 227 KB but measured 3 % slower.)  No divisions in the loop: one thread sustains ~1 TMA instruction per 400 cycles.
+        // ================= TMA producers: U boxes [U_ROWS snapshots][128 points]; each thread feeds the private stages of two quarters ======
+        // The stages of a quarter hold exactly one slab-tile, so the boxes of the NEXT slab-tile are requested as soon as the current ones
+        // are consumed; snapshots beyond U_STAGES * U_ROWS (none by default) are fetched by the epilogue threads themselves one slab ahead.
+        // No divisions in the loop: one thread sustains ~1 TMA instruction per 400 cycles.
         if (elect_one_sync()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmU) : "memory");
             const int h0 = (warp - 2) * 2;
@@ -322,6 +344,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         // ================================================ MMA issuer ================================================
         if (elect_one_sync()) {
             constexpr uint32_t idesc_g1 = make_idesc_bf16(BP, BT, 1, 1);
+            constexpr uint32_t idesc_g1_ts = make_idesc_bf16(BP, BT, 0, 1);  // A from TMEM: rows = lanes, K along columns
             constexpr uint32_t idesc_g4 = make_idesc_bf16(BT, KP, 1, 0);
             unsigned long long tm[6] = {0, 0, 0, 0, 0, 0};
             auto issue_g1 = [&](int it) {
@@ -340,8 +363,12 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 uint32_t acc = 0;
 #define G1_PAIR(PA, PB)                                                                                              \
     _Pragma("unroll") for (int ks = 0; ks < KP / 16; ++ks) {                                                          \
-        mma_bf16(tmem + TMEM_REC, desc_from(ga_lo + ((PA * G_PLANE + ks * 2048) >> 4), kDescHi),                      \
-                 desc_from(wa_lo + ((PB * W_PLANE + ks * 2048) >> 4), kDescHi), idesc_g1, acc);                       \
+        if (G1_TMEM)                                                                                                  \
+            mma_bf16_ts(tmem + TMEM_REC, tmem + TMEM_G + PA * (KP / 2) + ks * 8,                                      \
+                        desc_from(wa_lo + ((PB * W_PLANE + ks * 2048) >> 4), kDescHi), idesc_g1_ts, acc);             \
+        else                                                                                                          \
+            mma_bf16(tmem + TMEM_REC, desc_from(ga_lo + ((PA * G_PLANE + ks * 2048) >> 4), kDescHi),                  \
+                     desc_from(wa_lo + ((PB * W_PLANE + ks * 2048) >> 4), kDescHi), idesc_g1, acc);                   \
         acc = 1;                                                                                                      \
     }
 #ifndef EXP_NO_G1
@@ -485,13 +512,9 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         //      purpose (gv[] lives in local memory): this runs once per tile and straight-line code only thrashes the I-cache. ----
         float gv[KP / NQ];
         unsigned long long tl2[2] = {0, 0};
-        auto prefetch_lat = [&](long long tile_) {  // phi / P of a later tile -> L2, a tile ahead of their use (quarter h takes modes h, h+4)
-            const long long x_ = tile_ * BP + p;
-            for (int i = h; i < a.r; i += NQ) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.phi + (long long)i * a.ld + x_));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.P + (long long)i * a.ld + x_));
-            }
-        };
+        // quarter h owns the library PAIRS c = h, h+4, h+8, h+12 (terms 2c, 2c+1): a pair is one packed word of the TMEM-resident A
+        // operand of G1, and the interleave spreads the sin / cos / tanh terms (the last 3r of K) over the four quarters
+        auto term_of = [&](int jj) { return 2 * (h + (jj >> 1) * NQ) + (jj & 1); };
         auto eval_library = [&](long long tile_) {
             const long long x_ = tile_ * BP + p;
             const long long ce0 = now();
@@ -499,7 +522,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             const long long ce1 = now();
 #pragma unroll 1
             for (int jj = 0; jj < KP / NQ; ++jj) {
-                const int j = h + jj * NQ;
+                const int j = term_of(jj);
                 float v = 0.0f;
                 if (j < a.T) {
                     v = monomial(a.mt, j, lat, 1);
@@ -512,9 +535,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             }
             if (kDebug) { tl2[0] += ce1 - ce0; tl2[1] += now() - ce1; }
         };
-        auto store_library = [&]() {  // three bf16 planes, G_s[lib rows][p contiguous]
+        auto store_library = [&]() {  // bf16 planes: G_s[lib rows][p contiguous] (B of G4; A of G1 unless G1_TMEM) and TMEM [p lane][lib pairs]
             const uint32_t gs = sbase + G_OFF + (p >> 6) * (KP * 128);
             const uint32_t pb = (p & 63) * 2;
+            uint16_t pl[3][KP / NQ];
 #pragma unroll
             for (int jj = 0; jj < KP / NQ; ++jj) {
                 const float v = gv[jj];
@@ -522,10 +546,20 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 const float e1 = v - __bfloat162float(b1);
                 const __nv_bfloat16 b2 = __float2bfloat16_rn(e1);
                 const __nv_bfloat16 b3 = __float2bfloat16_rn(e1 - __bfloat162float(b2));
-                const uint32_t off = sw128(h + jj * NQ, pb);
-                st_shared_u16(gs + off, __bfloat16_as_ushort(b1));
-                st_shared_u16(gs + G_PLANE + off, __bfloat16_as_ushort(b2));
-                st_shared_u16(gs + 2 * G_PLANE + off, __bfloat16_as_ushort(b3));
+                pl[0][jj] = __bfloat16_as_ushort(b1); pl[1][jj] = __bfloat16_as_ushort(b2); pl[2][jj] = __bfloat16_as_ushort(b3);
+                const uint32_t off = sw128(term_of(jj), pb);
+                st_shared_u16(gs + off, pl[0][jj]);
+                st_shared_u16(gs + G_PLANE + off, pl[1][jj]);
+                if (!G1_TMEM) st_shared_u16(gs + 2 * G_PLANE + off, pl[2][jj]);
+            }
+            if (G1_TMEM) {
+#pragma unroll
+                for (int pa = 0; pa < 3; ++pa)
+#pragma unroll
+                    for (int cc = 0; cc < KP / NQ / 2; ++cc)
+                        tmem_st1(tmem + lane_addr + TMEM_G + pa * (KP / 2) + h + cc * NQ, (uint32_t)pl[pa][2 * cc] | ((uint32_t)pl[pa][2 * cc + 1] << 16));
+                tmem_st_wait();
+                tc_fence_before();
             }
             fence_async_smem();
             mbar_arrive(bar(G_FULL));
@@ -538,7 +572,6 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             const bool xin = x < a.n;
             long long cg0 = now();
             if (tl == 0) eval_library(tile);
-            if (tl + 1 < my_tiles) prefetch_lat(tile + gridDim.x);
             long long cg1 = now();
             if (tl > 0) mbar_wait(bar(G_EMPTY), (tl - 1) & 1, 9, tl);
             cg0 = now(); te[5] += cg0 - cg1;
