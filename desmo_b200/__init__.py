@@ -3,10 +3,10 @@
 Importing the package never touches the GPU; constructing a model / engine loads ``libdesmo_b200.so`` (built in-tree with
 nvcc) and fails loudly when it, or a CUDA device, is missing -- there is no CPU fallback.
 """
-from ._lib import DesmoError, PATH_AUTO, PATH_FP32, PATH_TC  # noqa: F401
+from ._lib import DesmoError, PATH_AUTO, PATH_FP32, PATH_GEMM, PATH_TC  # noqa: F401
 from .engine import REFERENCE_LRS, DesmoEngine  # noqa: F401
 from .model import DESMO, DESMOFourier  # noqa: F401
 from .trainer import DesmoTrainer, PlateauScheduler  # noqa: F401
 
 __all__ = ["DESMO", "DESMOFourier", "DesmoEngine", "DesmoTrainer", "PlateauScheduler", "DesmoError", "REFERENCE_LRS",
-           "PATH_AUTO", "PATH_FP32", "PATH_TC"]
+           "PATH_AUTO", "PATH_FP32", "PATH_TC", "PATH_GEMM"]

@@ -10,9 +10,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DESMO_B200_LIB") or os.path.join(HERE, "libdesmo_b200.so")  # override: kernel experiments (tools/variant.sh)
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "desmo_b200.h")
 
-PATH_AUTO, PATH_FP32, PATH_TC = 0, 1, 2
+PATH_AUTO, PATH_FP32, PATH_TC, PATH_GEMM = 0, 1, 2, 3
+PATH_NAMES = {1: "fp32 ffma", 2: "fused tcgen05 (bf16-split)", 3: "tcgen05 GEMM path (bf16-split)"}
 HYP_LR_GATES, HYP_LR_PHI, HYP_LR_Z, HYP_LR_OMEGA, HYP_LR_PERIOD, HYP_BETA, HYP_L1_LAMBDA, HYP_COUNT = range(8)
-MAX_R, MAX_P, MAX_K = 8, 7, 80
+MAX_R, MAX_P, MAX_K = 64, 7, 4096
 PRE_MAGNITUDE, PRE_SUBTRACT_MEAN, PRE_SCALE_SQRT_M = 1, 2, 4
 
 
@@ -35,6 +36,7 @@ SIGNATURES: Dict[str, tuple] = {
     "desmo_num_terms": (_i32, [_i32, _i32]),
     "desmo_padded_k": (_i32, [_i32, _i32]),
     "desmo_red_count": (_i64, [_SP]),
+    "desmo_selected_path": (_i32, [_SP]),
     "desmo_workspace_bytes": (C.c_int, [_SP, C.POINTER(C.c_size_t)]),
     "desmo_build_w": (C.c_int, [_SP] + [_vp] * 8),
     "desmo_fused_residual_grad": (C.c_int, [_SP] + [_vp] * 9),

@@ -41,6 +41,16 @@ static long long binom(int n, int k) {
     return v;
 }
 
+int count_terms(int r, int p) {
+    if (r < 1 || r > DESMO_MAX_R || p < 0 || p > DESMO_MAX_P) return -1;
+    long long T = 0;
+    for (int k = 0; k <= p; ++k) {  // calculate_number_of_terms, CYL:448-455
+        T += binom(r + k - 1, k);
+        if (T + 3 * r > DESMO_MAX_K) return -1;
+    }
+    return (int)T;
+}
+
 int build_mono_table(int r, int p, MonoTable* mt) {
     if (r < 1 || r > kMaxR || p < 0 || p > kMaxP) return -1;
     long long T = 0;
@@ -88,15 +98,33 @@ int validate_shape(const desmo_shape* s, Dims* d) {
         return DESMO_ERR_ARG;
     }
     if (s->nF < 0 || s->nF > 64) { set_error("nF=%d outside 0..64", s->nF); return DESMO_ERR_UNSUPPORTED; }
-    const int T = build_mono_table(s->r, s->polyorder, &d->mt);
+    const int T = count_terms(s->r, s->polyorder);
     if (T < 0) {
-        set_error("unsupported library: r=%d polyorder=%d (need 1<=r<=%d, 0<=p<=%d, T+3r<=%d)", s->r, s->polyorder, kMaxR, kMaxP, kMaxK);
+        set_error("unsupported library: r=%d polyorder=%d (need 1<=r<=%d, 0<=p<=%d, T+3r<=%d)", s->r, s->polyorder, DESMO_MAX_R, DESMO_MAX_P,
+                  DESMO_MAX_K);
         return DESMO_ERR_UNSUPPORTED;
     }
     d->T = T;
     d->K = T + 3 * s->r;
     d->Kp = (d->K + 15) / 16 * 16;
+    d->small = build_mono_table(s->r, s->polyorder, &d->mt) == T;  // within the fused kernels' limits (r <= 8, K <= 80)
+    if (s->path < DESMO_PATH_AUTO || s->path > DESMO_PATH_GEMM) { set_error("bad path %d", s->path); return DESMO_ERR_ARG; }
     return DESMO_OK;
+}
+
+// Which implementation runs this shape.  AUTO: the fused tcgen05 kernel where it applies (K <= 32, m <= 1024), else the GEMM path.
+int select_path(const desmo_shape* s, const Dims& d) {
+    const bool tc_ok = d.small && fused_tc_supported(s, d.Kp) != 0;
+    switch (s->path) {
+        case DESMO_PATH_AUTO: return tc_ok ? DESMO_PATH_TC : DESMO_PATH_GEMM;
+        case DESMO_PATH_TC:
+            if (!tc_ok) { set_error("fused tcgen05 path does not cover this shape (K=%d > 32 or mld=%d > 1024 or r=%d > 8)", d.K, s->mld, s->r); return -1; }
+            return DESMO_PATH_TC;
+        case DESMO_PATH_FP32:
+            if (!d.small) { set_error("FFMA path covers r <= %d, K <= %d (got r=%d, K=%d)", kMaxR, kMaxK, s->r, d.K); return -1; }
+            return DESMO_PATH_FP32;
+        default: return DESMO_PATH_GEMM;
+    }
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -107,20 +135,23 @@ int carve_workspace(const desmo_shape* s, const Dims& d, void* base, Workspace* 
     DESMO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     size_t off = 0;
     char* b = static_cast<char*>(base);
+    const int path = select_path(s, d);
+    if (path < 0) return DESMO_ERR_UNSUPPORTED;
+    const bool fused = path != DESMO_PATH_GEMM;  // per-CTA partial layouts of the fused kernels
     ws->Spart = reinterpret_cast<double*>(b + off); off = align_up(off + sizeof(double) * kMaxSlots * kScal, 256);
-    ws->Epart = reinterpret_cast<float*>(b + off);  off = align_up(off + sizeof(float) * (size_t)sms * d.Kp * s->mld, 256);
+    ws->Epart = reinterpret_cast<float*>(b + off);  off = align_up(off + (fused ? sizeof(float) * (size_t)sms * d.Kp * s->mld : 0), 256);
     ws->l1 = reinterpret_cast<float*>(b + off);     off = align_up(off + 256, 256);
-    ws->tc = reinterpret_cast<float*>(b + off);     off = align_up(off + sizeof(float) * 2 * (size_t)(d.Kp > 32 ? d.Kp : 32) * s->mld, 256);  // >= 3 bf16 planes [32][mld]
+    ws->tc = reinterpret_cast<float*>(b + off);     off = align_up(off + (fused ? sizeof(float) * 2 * (size_t)(d.Kp > 32 ? d.Kp : 32) * s->mld : 0), 256);  // >= 3 bf16 planes [32][mld]
     ws->gram = reinterpret_cast<float*>(b + off);   off = align_up(off + sizeof(float) * (size_t)sms * 128 * 128, 256);
     ws->Dacc = reinterpret_cast<float*>(b + off);   off = align_up(off + sizeof(float) * (size_t)d.Kp * s->ld, 256);
+    off = align_up(off, 1024);
+    ws->gemm = b + off;
+    if (!fused) off += gemm_workspace_bytes(s, d.T, d.K, d.Kp, nullptr, nullptr);
     ws->bytes = off;
     return DESMO_OK;
 }
 
-bool use_tc_path(const desmo_shape* s, const Dims& d) {
-    if (s->path == DESMO_PATH_FP32) return false;
-    return fused_tc_supported(s, d.Kp) != 0;
-}
+bool use_tc_path(const desmo_shape* s, const Dims& d) { return select_path(s, d) == DESMO_PATH_TC; }
 
 }  // namespace desmo
 
@@ -131,10 +162,10 @@ extern "C" {
 const char* desmo_last_error(void) { return g_err; }
 const char* desmo_version(void) { return "desmo_b200 0.1 (sm_100a)"; }
 
-int32_t desmo_num_terms(int32_t r, int32_t polyorder) { return build_mono_table(r, polyorder, nullptr); }
+int32_t desmo_num_terms(int32_t r, int32_t polyorder) { return count_terms(r, polyorder); }
 
 int32_t desmo_padded_k(int32_t r, int32_t polyorder) {
-    const int T = build_mono_table(r, polyorder, nullptr);
+    const int T = count_terms(r, polyorder);
     return T < 0 ? -1 : (T + 3 * r + 15) / 16 * 16;
 }
 
@@ -142,6 +173,12 @@ int64_t desmo_red_count(const desmo_shape* s) {
     Dims d;
     if (validate_shape(s, &d)) return -1;
     return (int64_t)d.Kp * s->mld + 1 + s->r * s->r + 3 * s->r;
+}
+
+int32_t desmo_selected_path(const desmo_shape* s) {
+    Dims d;
+    if (validate_shape(s, &d)) return -1;
+    return select_path(s, d);
 }
 
 int desmo_workspace_bytes(const desmo_shape* s, size_t* bytes) {
@@ -178,12 +215,13 @@ static int fused_dispatch(const desmo_shape* s, const float* U, const float* P, 
     if (!U || !P || !phi || !omega || !W || !dphi || !red || !workspace) { set_error("%s: null pointer", who); return DESMO_ERR_ARG; }
     Workspace ws;
     if ((rc = carve_workspace(s, d, workspace, &ws))) return rc;
-    if (s->path == DESMO_PATH_TC && !fused_tc_supported(s, d.Kp)) {
-        set_error("tcgen05 path does not support this shape (Kp=%d, mld=%d)", d.Kp, s->mld);
-        return DESMO_ERR_UNSUPPORTED;
+    switch (select_path(s, d)) {
+        case DESMO_PATH_TC: return fused_tc(s, d.mt, d.T, d.Kp, U, P, phi, omega, W, dphi, red, ws, (cudaStream_t)stream, supplied);
+        case DESMO_PATH_FP32: return fused_fp32(s, d.mt, d.T, d.Kp, U, P, phi, omega, W, dphi, red, ws, (cudaStream_t)stream, supplied);
+        case DESMO_PATH_GEMM:
+            return fused_gemm_path(s, d.T, d.K, d.Kp, U, P, phi, omega, W, dphi, red, ws.Dacc, ws.gemm, (cudaStream_t)stream, supplied);
+        default: return DESMO_ERR_UNSUPPORTED;
     }
-    if (use_tc_path(s, d)) return fused_tc(s, d.mt, d.T, d.Kp, U, P, phi, omega, W, dphi, red, ws, (cudaStream_t)stream, supplied);
-    return fused_fp32(s, d.mt, d.T, d.Kp, U, P, phi, omega, W, dphi, red, ws, (cudaStream_t)stream, supplied);
 }
 
 int desmo_fused_residual_grad(const desmo_shape* s, const float* U, const float* P, const float* phi, const float* omega,
@@ -265,6 +303,7 @@ int desmo_reconstruct(const desmo_shape* s, const float* P, const float* phi, co
     if (rc) return rc;
     if ((rc = device_ok())) return rc;
     if (!P || !phi || !omega || !W || !out) { set_error("desmo_reconstruct: null pointer"); return DESMO_ERR_ARG; }
+    if (!d.small) return reconstruct_gemm_path(s, d.T, d.K, d.Kp, P, phi, omega, W, out, (cudaStream_t)stream);
     EvalArgs a{};
     a.P = P; a.phi = phi; a.omega = omega; a.W = W; a.out = out; a.n = s->n; a.ld = s->ld; a.m = s->m; a.mld = s->mld;
     a.r = s->r; a.T = d.T; a.K = d.K; a.mt = d.mt;
@@ -277,6 +316,7 @@ int desmo_library_colnorm2(const desmo_shape* s, const float* P, const float* ph
     if (rc) return rc;
     if ((rc = device_ok())) return rc;
     if (!phi || !omega || !out_k) { set_error("desmo_library_colnorm2: null pointer"); return DESMO_ERR_ARG; }
+    if (!d.small) return colnorm2_gemm_path(s, d.T, d.K, P, phi, omega, out_k, (cudaStream_t)stream);
     EvalArgs a{};
     a.P = P; a.phi = phi; a.omega = omega; a.out = out_k; a.n = s->n; a.ld = s->ld; a.m = s->m; a.mld = s->mld;
     a.r = s->r; a.T = d.T; a.K = d.K; a.mt = d.mt;

@@ -8,9 +8,11 @@
 
 namespace desmo {
 
-constexpr int kMaxR = DESMO_MAX_R;
+// Limits of the fused kernels (FFMA and fused tcgen05): library table passed by value in the kernel parameters, per-mode register arrays.
+// Larger libraries (up to DESMO_MAX_R modes / DESMO_MAX_K terms) run on the GEMM path (gemm_path.cu), which has no such limits.
+constexpr int kMaxR = 8;
 constexpr int kMaxP = DESMO_MAX_P;
-constexpr int kMaxK = DESMO_MAX_K;
+constexpr int kMaxK = 80;
 constexpr int kMaxT = kMaxK;  // monomial columns that fit next to 3r trig columns
 constexpr int kMaxPairs = kMaxR * (kMaxR + 1) / 2;
 // per-CTA scalar partials (double): [0] sum r^2, [1 .. 1+r*r) Phi^T Phi, [1+r*r .. +3r) d omega
@@ -28,7 +30,8 @@ struct MonoTable {
 };
 
 struct Workspace {  // device-side carve-up of the caller's workspace; computed identically on the host
-    float* Epart;    // [slots_x][Kp][mld]
+    void* gemm;      // general-library path (gemm_path.cu), present when the fused tcgen05 kernel does not cover the shape
+    float* Epart;    // [slots_x][Kp][mld]   (fused kernels only)
     double* Spart;   // [kMaxSlots][kScal]
     float* Dacc;     // [Kp][ld]   (only when the time axis is chunked)
     float* l1;       // [1] sum |gates| before the update
@@ -94,7 +97,17 @@ int pod_project(const desmo_shape* s, const float* U, const float* V, const floa
 int preprocess(const desmo_shape* s, const void* V, int v_dtype, long long v_ld, int m_in, int t_stride, int d_in, int d_use, int flags,
                float* U, double* mean, cudaStream_t st);
 
-struct Dims { int T, K, Kp; MonoTable mt; };
+struct Dims { int T, K, Kp; bool small; MonoTable mt; };  // small: within the fused kernels' limits (mt valid)
+int count_terms(int r, int p);  // T = C(r+p, p) for 1 <= r <= DESMO_MAX_R, 0 <= p <= DESMO_MAX_P and T + 3r <= DESMO_MAX_K, else -1
+struct GemmWorkspace;
+size_t gemm_workspace_bytes(const desmo_shape* s, int T, int K, int Kp, uint8_t* base, GemmWorkspace* w);
+int fused_gemm_path(const desmo_shape* s, int T, int K, int Kp, const float* U, const float* P, const float* phi, const float* omega,
+                    const float* W, float* dphi, float* red, float* Dacc, void* gemm_ws, cudaStream_t st, bool supplied);
+int reconstruct_gemm_path(const desmo_shape* s, int T, int K, int Kp, const float* P, const float* phi, const float* omega, const float* W,
+                          float* out, cudaStream_t st);
+int colnorm2_gemm_path(const desmo_shape* s, int T, int K, const float* P, const float* phi, const float* omega, float* out_k, cudaStream_t st);
+int launch_update_phi_generic(const UpdateArgs& a, cudaStream_t st);
+int select_path(const desmo_shape* s, const Dims& d);  // DESMO_PATH_FP32 / _TC / _GEMM actually used, or <0 (error set)
 int validate_shape(const desmo_shape* s, Dims* d);
 int carve_workspace(const desmo_shape* s, const Dims& d, void* base, Workspace* ws);
 bool use_tc_path(const desmo_shape* s, const Dims& d);

@@ -197,11 +197,57 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
     }
 }
 
+// phi role for r > 8 (GEMM path): CTA tile of 128 points, Phi tile and the sign matrix of the ortho sub-gradient in shared memory.
+__global__ void __launch_bounds__(128) update_phi_generic_kernel(const UpdateArgs a) {
+    extern __shared__ float sm_g[];
+    const int r = a.r, tid = threadIdx.x;
+    float* gs = sm_g;             // [r][r]  sign(Phi_i . Phi_j), zero diagonal
+    float* lat_s = sm_g + r * r;  // [r][128]
+    const long long eoff = (long long)a.Kp * a.mld;
+    for (int e = tid; e < r * r; e += 128) gs[e] = (e / r == e % r) ? 0.0f : sgn(a.red[eoff + 1 + e]);
+    const int step = a.apply ? *a.step_dev : 1;
+    const float beta = a.hyper[DESMO_HYP_BETA];
+    const float clr = clr_of(a.hyper[DESMO_HYP_LR_PHI], step);
+    const long long ntiles = (a.n + 127) / 128;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long x = tile * 128 + tid;
+        __syncthreads();
+        for (int i = 0; i < r; ++i) lat_s[i * 128 + tid] = (x < a.n) ? a.phi[(long long)i * a.ld + x] * a.P[(long long)i * a.ld + x] : 0.0f;
+        __syncthreads();
+        if (x >= a.n) continue;
+        for (int i = 0; i < r; ++i) {
+            float o = 0.0f;
+            for (int j = 0; j < r; ++j) o = fmaf(gs[i * r + j], lat_s[j * 128 + tid], o);
+            const long long off = (long long)i * a.ld + x;
+            const float g = a.dphi[off] + beta * o * a.P[off];
+            if (a.apply) adamax(a.phi + off, a.phi_m + off, a.phi_u + off, g, clr);
+            else a.dphi_out[off] = g;
+        }
+    }
+}
+
+int launch_update_phi_generic(const UpdateArgs& a, cudaStream_t st) {
+    long long nb = (a.n + 127) / 128;
+    if (nb > 148 * 8) nb = 148 * 8;
+    const size_t smem = sizeof(float) * ((size_t)a.r * a.r + (size_t)a.r * 128);
+    DESMO_CUDA(cudaFuncSetAttribute(update_phi_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    update_phi_generic_kernel<<<(unsigned)nb, 128, smem, st>>>(a);
+    DESMO_CUDA(cudaGetLastError());
+    return DESMO_OK;
+}
+
 int launch_update(const UpdateArgs& a, cudaStream_t st) {
     long long nb = (a.n + 1023) / 1024;  // 4 points per thread in the phi role
     if (nb > 148 * 8) nb = 148 * 8;
     if (nb < 1) nb = 1;
     if (a.nF > 64) { set_error("update: nF > 64 not supported"); return DESMO_ERR_UNSUPPORTED; }
+    if (a.r > kMaxR) {
+        // the phi role of update_kernel keeps per-mode register arrays (r <= 8); larger r: its own kernel, launched FIRST because the
+        // rows / gates / omega roles do not touch phi and this one reads only `red`, dphi, P, phi
+        int rc = launch_update_phi_generic(a, st);
+        if (rc) return rc;
+        nb = 0;
+    }
     update_kernel<<<(unsigned)(a.K + 1 + nb), 256, 0, st>>>(a);
     DESMO_CUDA(cudaGetLastError());
     return DESMO_OK;

@@ -43,6 +43,9 @@ class DesmoEngine:
         self.n_global = int(n_global) if n_global else self.n
         self.shape = make_shape(self.n, self.m, self.r, self.polyorder, self.nF, self.n_global, path)
         self.ld, self.mld = self.shape.ld, self.shape.mld
+        self.path_used = int(self.lib.desmo_selected_path(C.byref(self.shape)))  # 1 FFMA, 2 fused tcgen05, 3 tcgen05 GEMM path
+        if self.path_used < 0:
+            raise _lib.DesmoError(self.lib.desmo_last_error().decode(errors="replace"))
         f32 = dict(dtype=torch.float32, device=self.device)
         z = lambda *s: torch.zeros(*s, **f32)  # noqa: E731
         self.U: Optional[torch.Tensor] = None
@@ -102,8 +105,8 @@ class DesmoEngine:
 
     # ------------------------------------------------------------------ launches
     def uses_tensor_cores(self) -> bool:
-        """True when desmo_fused_residual_grad dispatches to the tcgen05 kernel for this shape / path."""
-        return self.shape.path != _lib.PATH_FP32 and self.Kp <= 32 and self.mld <= 1024
+        """True when desmo_fused_residual_grad dispatches to a tcgen05 implementation (fused kernel or GEMM path)."""
+        return self.path_used in (_lib.PATH_TC, _lib.PATH_GEMM)
 
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream

@@ -41,13 +41,14 @@ extern "C" {
 #define DESMO_ERR_UNSUPPORTED 2 /* (r, p, K, m) outside what the kernels are instantiated for */
 #define DESMO_ERR_CUDA 3      /* CUDA runtime error, no device, or not sm_100 */
 
-#define DESMO_MAX_R 8
-#define DESMO_MAX_P 7
-#define DESMO_MAX_K 80
+#define DESMO_MAX_R 64     /* modes (r_DESMO) */
+#define DESMO_MAX_P 7      /* POOL_DATA supports polyorder <= 7 (CYL:376-434) */
+#define DESMO_MAX_K 4096   /* library terms K = C(r+p, p) + 3r, e.g. (r, p) = (8, 3): 189, (32, 2): 657, (64, 2): 2337 */
 
-#define DESMO_PATH_AUTO 0
-#define DESMO_PATH_FP32 1  /* FFMA path */
-#define DESMO_PATH_TC 2    /* tcgen05 path, 3-way bf16 split (fp32-grade accuracy) */
+#define DESMO_PATH_AUTO 0  /* fused tcgen05 kernel when K <= 32 and m <= 1024, else the tcgen05 GEMM path */
+#define DESMO_PATH_FP32 1  /* FFMA path (K <= 80, r <= 8): independent implementation kept for cross-checks */
+#define DESMO_PATH_TC 2    /* fused tcgen05 kernel (K <= 32, m <= 1024), bf16-split operands (fp32-grade accuracy) */
+#define DESMO_PATH_GEMM 3  /* general libraries (any K <= DESMO_MAX_K, r <= DESMO_MAX_R): three tcgen05 GEMMs per chunk of points */
 
 typedef struct desmo_shape {
     int64_t n;        /* mesh points owned by this rank (rows of the reference's X) */
@@ -78,6 +79,8 @@ const char* desmo_version(void);
 int32_t desmo_num_terms(int32_t r, int32_t polyorder);
 int32_t desmo_padded_k(int32_t r, int32_t polyorder);
 int64_t desmo_red_count(const desmo_shape* s);            /* number of floats in `red` */
+/* The implementation desmo_fused_residual_grad dispatches this shape to: DESMO_PATH_FP32 / _TC / _GEMM, or <0 if unsupported. */
+int32_t desmo_selected_path(const desmo_shape* s);
 int desmo_workspace_bytes(const desmo_shape* s, size_t* bytes);
 
 /* Library evaluation, temporal side: W = diag(gates) * rows  (CYL:548 `c_coef *`, CYL:565-567 `*_coef_list[i] *`);

@@ -25,8 +25,11 @@ def test_library_term_counts_match_reference_facts():
         assert lib.desmo_num_terms(r, p) == orc.number_of_terms(r, p)
         assert lib.desmo_padded_k(r, p) % 16 == 0 and lib.desmo_padded_k(r, p) >= orc.number_of_terms(r, p) + 3 * r
     assert lib.desmo_num_terms(8, 2) == 45 and lib.desmo_padded_k(8, 2) == 80  # BASELINE's "8 modes": K = 69
-    assert lib.desmo_num_terms(8, 3) < 0  # K = 189 > DESMO_MAX_K: reported as unsupported, never silently truncated
-    assert lib.desmo_num_terms(2, 8) < 0 and lib.desmo_num_terms(0, 2) < 0
+    # BASELINE's larger libraries: "8 modes" with p = 3, "32 modes", the sweep's r = 64 (GEMM path)
+    assert lib.desmo_num_terms(8, 3) == 165 and lib.desmo_num_terms(32, 2) == 561 and lib.desmo_num_terms(64, 2) == 2145
+    assert lib.desmo_padded_k(32, 2) == 672
+    assert lib.desmo_num_terms(64, 3) < 0  # K = 48097 > DESMO_MAX_K: reported as unsupported, never silently truncated
+    assert lib.desmo_num_terms(2, 8) < 0 and lib.desmo_num_terms(0, 2) < 0 and lib.desmo_num_terms(65, 1) < 0
 
 
 def test_shape_validation_and_error_strings():
@@ -38,6 +41,11 @@ def test_shape_validation_and_error_strings():
     K, Kp = 27, 32
     assert lib.desmo_red_count(ctypes.byref(ok)) == Kp * ok.mld + 1 + 16 + 12
     assert ok.ld % 128 == 0 and ok.mld % 16 == 0
+    # dispatch: fused tcgen05 kernel for K <= 32, m <= 1024; GEMM path beyond; explicit paths are refused where they do not apply
+    sel = lambda *a, **k: lib.desmo_selected_path(ctypes.byref(_lib.make_shape(*a, **k)))  # noqa: E731
+    assert sel(1000, 100, 4, 2) == _lib.PATH_TC and sel(1000, 100, 4, 3) == _lib.PATH_GEMM and sel(1000, 2000, 4, 2) == _lib.PATH_GEMM
+    assert sel(1000, 100, 32, 2) == _lib.PATH_GEMM and sel(1000, 100, 4, 3, path=_lib.PATH_FP32) == _lib.PATH_FP32
+    assert sel(1000, 100, 4, 3, path=_lib.PATH_TC) < 0 and sel(1000, 100, 32, 2, path=_lib.PATH_FP32) < 0
 
 
 def test_no_cpu_fallback():

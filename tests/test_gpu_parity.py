@@ -19,14 +19,20 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 GRAD_TOL = {"gates": 1e-5, "rows": 1e-5, "coefs": 1e-5, "periods": 5e-5, "phi": 5e-5, "omega": 5e-5}
-PATHS = [1, 2]  # DESMO_PATH_FP32 (FFMA) and DESMO_PATH_TC (tcgen05, bf16x3 split)
+PATHS = [1, 2, 3]  # DESMO_PATH_FP32 (FFMA), DESMO_PATH_TC (fused tcgen05 kernel), DESMO_PATH_GEMM (tcgen05 GEMM path, any library)
+
+
+def _skip_unless_covered(path, K, r, m):
+    if path == 2 and (K > 32 or m > 1024 or r > 8):
+        pytest.skip("the fused tcgen05 kernel covers K <= 32, m <= 1024 (larger shapes run on the GEMM path)")
+    if path == 1 and (K > 80 or r > 8):
+        pytest.skip("the FFMA path covers K <= 80, r <= 8")
 
 
 def _engine(prm, modes, snap, path=1, **kw):
     from desmo_b200 import DesmoEngine
 
-    if path == 2 and (prm.K > 32 or prm.m > 1024):
-        pytest.skip("tcgen05 path covers K <= 32, m <= 1024 (larger shapes run on the FFMA path)")
+    _skip_unless_covered(path, prm.K, prm.r, prm.m)
     e = DesmoEngine(prm.n, prm.m, prm.polyorder, prm.r, nF=prm.nF or None, device=torch.device("cuda:0"), path=path, **kw)
     load_engine(e, prm, modes, snap)
     return e
@@ -81,6 +87,12 @@ CASES = [  # (kind, n, m, r, p, nF) -- ragged sizes, single tile, multi tile, ch
     ("cylinder", 700, 90, 8, 2, 4),         # 8 modes, Fourier temporal library
     ("channel", 16384, 1000, 4, 2, None),   # C3 script shape (TURB): 128 point tiles x 8 time slabs on the tcgen05 path
     ("aneurysm", 27000, 1000, 4, 2, None),  # C4 script shape (ANEU): ragged last tile, ragged last slab
+    ("cylinder", 3961, 1001, 8, 3, None),   # C1 with "8 modes", p = 3: K = 189 (GEMM path)
+    ("channel", 4096, 600, 32, 2, None),    # "32 modes": T = 561, K = 657 (GEMM path), 3 library tiles x 5 snapshot tiles
+    ("channel", 16384, 1000, 32, 2, None),  # C3 with BASELINE's 32 modes at the script's mesh / snapshot shape
+    ("channel", 20000, 300, 16, 1, 6),      # r = 16 Fourier, p = 1: K = 65; two chunks of points (partial sums accumulate over chunks)
+    ("channel", 2000, 130, 64, 1, None),    # r = 64 (the sweep's largest mode count), p = 1: K = 257
+    ("cylinder", 900, 2100, 4, 2, None),    # more than 1024 snapshots: beyond the fused kernel's TMEM budget
 ]
 
 
@@ -212,8 +224,7 @@ def test_threshold_sweep_matches_reference_golden(name, path):
     from desmo_b200.sparsify import threshold_sweep
 
     fx, meta, modes, snap, prm = golden_case(name)
-    if path == 2 and prm.K > 32:
-        pytest.skip("K > 32")
+    _skip_unless_covered(path, prm.K, prm.r, prm.m)
     dev = torch.device("cuda:0")
     if prm.fourier:
         model = DESMOFourier(prm.n, prm.m, prm.polyorder, prm.r, 10.0, prm.nF, period_init=meta["period_init"], pod_modes=modes, device=dev, path=path)
