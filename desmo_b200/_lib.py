@@ -53,6 +53,8 @@ SIGNATURES: Dict[str, tuple] = {
     "desmo_pod_project": (C.c_int, [_SP] + [_vp] * 5),
     "desmo_preprocess": (C.c_int, [_SP, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "desmo_session_create": (C.c_int, [_i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
+    "desmo_session_create_sharded": (C.c_int, [_i64, _i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
+    "desmo_session_set_allreduce": (C.c_int, [_vp, _vp, _vp]),
     "desmo_session_destroy": (C.c_int, [_vp]),
     "desmo_session_set_pod_host": (C.c_int, [_vp, _vp]),
     "desmo_session_set_params_host": (C.c_int, [_vp] * 6),
@@ -93,6 +95,37 @@ def load(build_if_missing: bool = True):
         fn.restype, fn.argtypes = res, args
     _lib = lib
     return lib
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, _vp, _i64, _vp, _vp)  # desmo_allreduce_fn
+
+
+def torch_allreduce_hook(group=None):
+    """A desmo_allreduce_fn that sums the session's `red` buffer with torch.distributed (NCCL) on the session's own stream.
+    Keep the returned object alive as long as the session uses it."""
+    import torch
+    import torch.distributed as dist
+
+    class _Dev:  # exposes the raw device pointer to torch without a copy
+        def __init__(self, ptr, count):
+            self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+    cache = {}
+
+    def hook(ptr, count, stream, user):
+        try:
+            key = (ptr, count)
+            if key not in cache:
+                cache[key] = torch.as_tensor(_Dev(ptr, count), device=torch.device("cuda", torch.cuda.current_device()))
+            with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+                dist.all_reduce(cache[key], group=group)
+            return 0
+        except Exception as ex:  # a Python exception must not unwind through the C caller
+            import sys
+            print(f"desmo_b200 all-reduce hook failed: {ex}", file=sys.stderr)
+            return 1
+
+    return ALLREDUCE_FN(hook)
 
 
 def check(rc: int, what: str = "") -> None:

@@ -20,6 +20,8 @@ struct desmo_session {
     int32_t* step = nullptr;
     void* ws = nullptr;
     float* pinned_losses = nullptr;
+    desmo_allreduce_fn allreduce = nullptr;  // multi-rank sessions: sums `red` over the ranks on the session's stream
+    void* allreduce_user = nullptr;
     std::vector<void*> allocs;
 };
 
@@ -72,10 +74,22 @@ static int session_build(desmo_session* ss) {
 }
 
 int desmo_session_create(int64_t n, int32_t m, int32_t r, int32_t polyorder, int32_t nF, int32_t path, desmo_session** out) {
+    return desmo_session_create_sharded(n, n, m, r, polyorder, nF, path, out);
+}
+
+int desmo_session_set_allreduce(desmo_session* ss, desmo_allreduce_fn fn, void* user) {
+    if (!ss) { set_error("desmo_session_set_allreduce: null"); return DESMO_ERR_ARG; }
+    ss->allreduce = fn;
+    ss->allreduce_user = user;
+    return DESMO_OK;
+}
+
+int desmo_session_create_sharded(int64_t n, int64_t n_global, int32_t m, int32_t r, int32_t polyorder, int32_t nF, int32_t path,
+                                 desmo_session** out) {
     if (!out) { set_error("desmo_session_create: null out"); return DESMO_ERR_ARG; }
     *out = nullptr;
     desmo_session* ss = new desmo_session();
-    ss->s.n = n; ss->s.n_global = n; ss->s.ld = (n + 255) / 256 * 256; ss->s.m = m; ss->s.mld = (m + 15) / 16 * 16;
+    ss->s.n = n; ss->s.n_global = n_global; ss->s.ld = (n + 255) / 256 * 256; ss->s.m = m; ss->s.mld = (m + 15) / 16 * 16;
     ss->s.r = r; ss->s.polyorder = polyorder; ss->s.nF = nF; ss->s.path = path;
     int rc = validate_shape(&ss->s, &ss->d);
     if (!rc) rc = device_ok();
@@ -156,6 +170,10 @@ static int session_step_device(desmo_session* ss) {
     if (rc) return rc;
     rc = desmo_fused_residual_grad(s, ss->U, ss->P, ss->phi, ss->omega, ss->W, ss->dphi, ss->red, ss->ws, ss->st);
     if (rc) return rc;
+    if (s->n_global != s->n) {  // this rank owns a slab of the points: the one exchange of the step
+        if (!ss->allreduce) { set_error("sharded session (n_global != n) without an all-reduce hook: call desmo_session_set_allreduce"); return DESMO_ERR_ARG; }
+        if (ss->allreduce(ss->red, desmo_red_count(s), ss->st, ss->allreduce_user)) { set_error("all-reduce hook failed"); return DESMO_ERR_CUDA; }
+    }
     return desmo_adamax_update(s, ss->red, ss->dphi, ss->P, ss->phi, ss->phi_m, ss->phi_u, ss->gates, ss->gates_m, ss->gates_u, ss->rows,
                                ss->rows_m, ss->rows_u, ss->coefs, ss->coefs_m, ss->coefs_u, ss->periods, ss->periods_m, ss->periods_u,
                                ss->omega, ss->omega_m, ss->omega_u, ss->hyper, ss->step, ss->losses, ss->ws, ss->st);

@@ -86,8 +86,11 @@ class DesmoTrainer:
         """One epoch (CYL:706-778).  Returns (mse, ortho, l1, total) on scheduler epochs, else None (no host sync)."""
         if snapshot is not None:
             self.engine.set_snapshot(snapshot)
-        if self.epoch % self.sched_every == 0 and hasattr(self.model, "sync_parameters"):
-            self.model.sync_parameters()  # user code may have rebound param.data (CYL:1219-1226); cheap, only on scheduler epochs
+        if self.epoch % 256 == 0 and hasattr(self.model, "sync_parameters"):
+            # user code may have rebound param.data (the reference's sweep does, CYL:1219-1226).  The check walks every Parameter
+            # (~2 us each, 1400 of them at r = 32), so the hot loop pays it on the first epoch and every 256th only; forward(),
+            # mse_loss() and the sparsify sweeps check on every call.
+            self.model.sync_parameters()
         self._launch()
         out = None
         if self.epoch % self.sched_every == 0:

@@ -176,6 +176,13 @@ int desmo_preprocess(const desmo_shape* s, const void* V, int32_t v_dtype, int64
  * {mse, ortho, l1, total}.  Synchronous. */
 typedef struct desmo_session desmo_session;
 int desmo_session_create(int64_t n, int32_t m, int32_t r, int32_t polyorder, int32_t nF, int32_t path, desmo_session** out);
+/* Multi-GPU (one process per GPU, each owning a slab of n of the n_global mesh points): the session calls the
+ * hook between the fused pass and the update; it must sum red_device[0..count) over all ranks in place, enqueued on `stream` (e.g.
+ * ncclAllReduce, or torch.distributed.all_reduce under that stream) and return 0.  Required when n_global != n. */
+typedef int (*desmo_allreduce_fn)(float* red_device, int64_t count, void* stream, void* user);
+int desmo_session_create_sharded(int64_t n, int64_t n_global, int32_t m, int32_t r, int32_t polyorder, int32_t nF, int32_t path,
+                                 desmo_session** out);
+int desmo_session_set_allreduce(desmo_session* ss, desmo_allreduce_fn fn, void* user);
 int desmo_session_destroy(desmo_session* ss);
 int desmo_session_set_pod_host(desmo_session* ss, const double* pod_host /*[n][r] fp64*/);
 int desmo_session_set_params_host(desmo_session* ss, const float* phi /*[r][n]*/, const float* gates /*[K]*/,
