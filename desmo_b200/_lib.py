@@ -41,6 +41,8 @@ SIGNATURES: Dict[str, tuple] = {
     "desmo_build_w": (C.c_int, [_SP] + [_vp] * 8),
     "desmo_fused_residual_grad": (C.c_int, [_SP] + [_vp] * 9),
     "desmo_recon_backward": (C.c_int, [_SP] + [_vp] * 9),
+    "desmo_fused_residual_grad_begin": (C.c_int, [_SP] + [_vp] * 9),
+    "desmo_fused_residual_grad_finish": (C.c_int, [_SP] + [_vp] * 9),
     "desmo_adamax_update": (C.c_int, [_SP] + [_vp] * 26),
     "desmo_assemble_grads": (C.c_int, [_SP] + [_vp] * 17),
     "desmo_reconstruct": (C.c_int, [_SP] + [_vp] * 6),

@@ -207,7 +207,7 @@ int desmo_build_w(const desmo_shape* s, const float* gates, float* rows, const f
 }
 
 static int fused_dispatch(const desmo_shape* s, const float* U, const float* P, const float* phi, const float* omega, const float* W,
-                          float* dphi, float* red, void* workspace, void* stream, bool supplied, const char* who) {
+                          float* dphi, float* red, void* workspace, void* stream, bool supplied, const char* who, int phase = 0) {
     Dims d;
     int rc = validate_shape(s, &d);
     if (rc) return rc;
@@ -216,9 +216,12 @@ static int fused_dispatch(const desmo_shape* s, const float* U, const float* P, 
     Workspace ws;
     if ((rc = carve_workspace(s, d, workspace, &ws))) return rc;
     switch (select_path(s, d)) {
-        case DESMO_PATH_TC: return fused_tc(s, d.mt, d.T, d.Kp, U, P, phi, omega, W, dphi, red, ws, (cudaStream_t)stream, supplied);
-        case DESMO_PATH_FP32: return fused_fp32(s, d.mt, d.T, d.Kp, U, P, phi, omega, W, dphi, red, ws, (cudaStream_t)stream, supplied);
+        case DESMO_PATH_TC: return fused_tc(s, d.mt, d.T, d.Kp, U, P, phi, omega, W, dphi, red, ws, (cudaStream_t)stream, supplied, phase);
+        case DESMO_PATH_FP32:
+            if (phase == 2) return DESMO_OK;  // the other paths do everything in the first phase
+            return fused_fp32(s, d.mt, d.T, d.Kp, U, P, phi, omega, W, dphi, red, ws, (cudaStream_t)stream, supplied);
         case DESMO_PATH_GEMM:
+            if (phase == 2) return DESMO_OK;
             return fused_gemm_path(s, d.T, d.K, d.Kp, U, P, phi, omega, W, dphi, red, ws.Dacc, ws.gemm, (cudaStream_t)stream, supplied);
         default: return DESMO_ERR_UNSUPPORTED;
     }
@@ -227,6 +230,16 @@ static int fused_dispatch(const desmo_shape* s, const float* U, const float* P, 
 int desmo_fused_residual_grad(const desmo_shape* s, const float* U, const float* P, const float* phi, const float* omega,
                               const float* W, float* dphi, float* red, void* workspace, void* stream) {
     return fused_dispatch(s, U, P, phi, omega, W, dphi, red, workspace, stream, false, "desmo_fused_residual_grad");
+}
+
+int desmo_fused_residual_grad_begin(const desmo_shape* s, const float* U, const float* P, const float* phi, const float* omega,
+                                    const float* W, float* dphi, float* red, void* workspace, void* stream) {
+    return fused_dispatch(s, U, P, phi, omega, W, dphi, red, workspace, stream, false, "desmo_fused_residual_grad_begin", 1);
+}
+
+int desmo_fused_residual_grad_finish(const desmo_shape* s, const float* U, const float* P, const float* phi, const float* omega,
+                                     const float* W, float* dphi, float* red, void* workspace, void* stream) {
+    return fused_dispatch(s, U, P, phi, omega, W, dphi, red, workspace, stream, false, "desmo_fused_residual_grad_finish", 2);
 }
 
 int desmo_recon_backward(const desmo_shape* s, const float* grad_recon, const float* P, const float* phi, const float* omega,

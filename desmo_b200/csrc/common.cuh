@@ -80,7 +80,8 @@ int build_w(const desmo_shape* s, int K, int Kp, const float* gates, float* rows
 int fused_fp32(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const float* U, const float* P, const float* phi,
                const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st, bool supplied = false);
 int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const float* U, const float* P, const float* phi,
-             const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st, bool supplied = false);
+             const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st, bool supplied = false,
+             int phase = 0);
 int fused_tc_supported(const desmo_shape* s, int Kp);
 int tc_debug_read(uint64_t* out, int count);
 int fused_event_ms(float* ms);

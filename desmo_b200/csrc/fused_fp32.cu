@@ -366,23 +366,28 @@ static cudaError_t chain_rule_dispatch(const FusedArgs& a, int slot_base, int gc
 // Deterministic second stage: sum the per-CTA partials in a fixed order into `red`.
 // 32 outputs per CTA, 8 warps: warp w sums the partials b = w, w+8, ... of 32 consecutive outputs (coalesced), the eight sums are
 // added in warp order -- a fixed order, so the result does not depend on scheduling.
+// what: 1 = the E part only, 2 = the scalar tail only (one CTA), 3 = both.  The split lets a multi-GPU step all-reduce E on a side
+// stream while the chain-rule kernel is still producing the scalars (desmo_fused_residual_grad_begin / _finish).
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ Epart, int nx, long long ecount,
-                                                              const double* __restrict__ Spart, int nslots, int r, float* __restrict__ red) {
+                                                              const double* __restrict__ Spart, int nslots, int r, float* __restrict__ red,
+                                                              int what) {
     __shared__ float part_s[8][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long o = (long long)blockIdx.x * 32 + lane;
-    float s = 0.0f;
-    if (o < ecount)
-        for (int b = w; b < nx; b += 8) s += __ldg(Epart + (long long)b * ecount + o);
-    part_s[w][lane] = s;
-    __syncthreads();
-    if (w == 0 && o < ecount) {
-        float t = part_s[0][lane];
+    if (what & 1) {
+        float s = 0.0f;
+        if (o < ecount)
+            for (int b = w; b < nx; b += 8) s += __ldg(Epart + (long long)b * ecount + o);
+        part_s[w][lane] = s;
+        __syncthreads();
+        if (w == 0 && o < ecount) {
+            float t = part_s[0][lane];
 #pragma unroll
-        for (int k = 1; k < 8; ++k) t += part_s[k][lane];
-        red[o] = t;
+            for (int k = 1; k < 8; ++k) t += part_s[k][lane];
+            red[o] = t;
+        }
     }
-    if (blockIdx.x == 0 && threadIdx.x < kScal) {
+    if ((what & 2) && blockIdx.x == 0 && threadIdx.x < kScal) {
         const int i = threadIdx.x;
         double s = 0.0;
         for (int b = 0; b < nslots; ++b) s += Spart[(long long)b * kScal + i];
@@ -402,8 +407,10 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     }
 }
 
-void reduce_partials_launch(const float* Epart, int nx, long long ecount, const double* Spart, int nslots, int r, float* red, cudaStream_t st) {
-    reduce_partials_kernel<<<(unsigned)((ecount + 31) / 32), 256, 0, st>>>(Epart, nx, ecount, Spart, nslots, r, red);
+void reduce_partials_launch(const float* Epart, int nx, long long ecount, const double* Spart, int nslots, int r, float* red, cudaStream_t st,
+                            int what) {
+    const unsigned grid = (what & 1) ? (unsigned)((ecount + 31) / 32) : 1u;
+    reduce_partials_kernel<<<grid, 256, 0, st>>>(Epart, nx, ecount, Spart, nslots, r, red, what);
 }
 
 // Chain rule for a D matrix left in ws.Dacc by the tensor-core kernel (same kernel the chunked FFMA path uses).
@@ -493,7 +500,7 @@ int fused_fp32(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const f
     }
     if (rc) return rc;
     const long long ecount = (long long)Kp * s->mld;
-    reduce_partials_kernel<<<(unsigned)((ecount + 31) / 32), 256, 0, st>>>(ws.Epart, gx, ecount, ws.Spart, nslots, s->r, red);
+    reduce_partials_kernel<<<(unsigned)((ecount + 31) / 32), 256, 0, st>>>(ws.Epart, gx, ecount, ws.Spart, nslots, s->r, red, 3);
     DESMO_CUDA(cudaGetLastError());
     return DESMO_OK;
 }

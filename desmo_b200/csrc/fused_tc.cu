@@ -780,14 +780,30 @@ int fused_tc_supported(const desmo_shape* s, int Kp) {
     return (Kp <= tc::KP && s->mld <= tc::MAXSLAB * tc::BT && s->ld % 128 == 0 && s->mld % 8 == 0) ? 1 : 0;
 }
 
-void reduce_partials_launch(const float* Epart, int nx, long long ecount, const double* Spart, int nslots, int r, float* red, cudaStream_t st);
+void reduce_partials_launch(const float* Epart, int nx, long long ecount, const double* Spart, int nslots, int r, float* red, cudaStream_t st,
+                            int what);
 int chain_rule_launch(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const float* P, const float* phi, const float* omega, float* dphi,
                       const Workspace& ws, int slot_base, int* nslots, cudaStream_t st);
 
+// phase: 0 = the whole pass; 1 = the dominant kernel + the E part of `red` (final for this rank when it returns); 2 = chain rule + the
+// scalar tail of `red` (needs the per-CTA partials phase 1 left in the workspace).
 int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const float* U, const float* P, const float* phi,
-             const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st, bool supplied) {
+             const float* omega, const float* W, float* dphi, float* red, const Workspace& ws, cudaStream_t st, bool supplied, int phase) {
     (void)W;
     if (!fused_tc_supported(s, Kp)) { set_error("tcgen05 path: unsupported shape"); return DESMO_ERR_UNSUPPORTED; }
+    if (phase == 2) {
+        int dev2 = 0, sms2 = 0;
+        DESMO_CUDA(cudaGetDevice(&dev2));
+        DESMO_CUDA(cudaDeviceGetAttribute(&sms2, cudaDevAttrMultiProcessorCount, dev2));
+        const long long ntiles2 = s->ld / tc::BP;
+        const int grid2 = (int)(ntiles2 < sms2 ? ntiles2 : sms2);
+        int nchain2 = 0;
+        int rc2 = chain_rule_launch(s, mt, T, Kp, P, phi, omega, dphi, ws, grid2, &nchain2, st);
+        if (rc2) return rc2;
+        reduce_partials_launch(ws.Epart, grid2, (long long)Kp * s->mld, ws.Spart, grid2 + nchain2, s->r, red, st, 2);
+        DESMO_CUDA(cudaGetLastError());
+        return DESMO_OK;
+    }
     EncodeTiledFn enc = encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled not available"); return DESMO_ERR_CUDA; }
     int dev = 0, sms = 0;
@@ -854,10 +870,15 @@ int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const flo
     }
     fused_event_record(1, st);
     DESMO_CUDA(cudaGetLastError());
+    if (phase == 1) {
+        reduce_partials_launch(ws.Epart, grid, (long long)Kp * s->mld, ws.Spart, grid, s->r, red, st, 1);
+        DESMO_CUDA(cudaGetLastError());
+        return DESMO_OK;
+    }
     int nchain = 0;
     int rc = chain_rule_launch(s, mt, T, Kp, P, phi, omega, dphi, ws, grid, &nchain, st);
     if (rc) return rc;
-    reduce_partials_launch(ws.Epart, grid, (long long)Kp * s->mld, ws.Spart, grid + nchain, s->r, red, st);
+    reduce_partials_launch(ws.Epart, grid, (long long)Kp * s->mld, ws.Spart, grid + nchain, s->r, red, st, 3);
     DESMO_CUDA(cudaGetLastError());
     return DESMO_OK;
 }

@@ -72,6 +72,7 @@ class DesmoEngine:
             check(self.lib.desmo_workspace_bytes(C.byref(self.shape), C.byref(nbytes)), "desmo_workspace_bytes")
         self.workspace = torch.zeros(nbytes.value, dtype=torch.uint8, device=self.device)
         self.launches_per_step = 0
+        self._side: Optional[torch.cuda.Stream] = None
         self.set_hyper(REFERENCE_LRS, 1e-3, 1e-4)
 
     # ------------------------------------------------------------------ inputs
@@ -136,12 +137,34 @@ class DesmoEngine:
             _ptr(self.omega), _ptr(self.omega_m), _ptr(self.omega_u), _ptr(self.hyper), _ptr(self.step_dev), _ptr(self.losses),
             _ptr(self.workspace), self._stream()), "desmo_adamax_update")
 
+    def _sharded(self) -> bool:
+        return self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized() and self.n_global != self.n)
+
     def train_step(self) -> None:
-        """forward + losses + backward + optimizer.step of CYL:711-768; losses land in self.losses (device)."""
+        """forward + losses + backward + optimizer.step of CYL:711-768; losses land in self.losses (device).
+
+        Multi-GPU: the K x m block of `red` (E = G^T R) is final as soon as the dominant kernel has run, so its all-reduce is issued
+        on a side stream and overlaps the chain-rule kernel; only the 1 + r^2 + 3r scalars are reduced afterwards."""
         with torch.cuda.device(self.device):
             self.build_w(True)
-            self.fused_residual_grad()
-            self.all_reduce()
+            if not self._sharded():
+                self.fused_residual_grad()
+            else:
+                if self.U is None:
+                    raise _lib.DesmoError("no snapshot matrix set (call set_snapshot)")
+                args = (C.byref(self.shape), _ptr(self.U), _ptr(self.P), _ptr(self.phi), _ptr(self.omega), _ptr(self.W), _ptr(self.dphi),
+                        _ptr(self.red), _ptr(self.workspace))
+                main = torch.cuda.current_stream(self.device)
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=self.device)
+                ecount = self.Kp * self.mld
+                check(self.lib.desmo_fused_residual_grad_begin(*args, main.cuda_stream), "desmo_fused_residual_grad_begin")
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    torch.distributed.all_reduce(self.red[:ecount], group=self.pg)
+                check(self.lib.desmo_fused_residual_grad_finish(*args, main.cuda_stream), "desmo_fused_residual_grad_finish")
+                torch.distributed.all_reduce(self.red[ecount:], group=self.pg)
+                main.wait_stream(self._side)
             self.adamax_update()
 
     def gradients(self, beta: Optional[float] = None, l1_lambda: Optional[float] = None) -> dict:

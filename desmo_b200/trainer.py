@@ -126,7 +126,12 @@ class DesmoTrainer:
         if sd.get("model") is not None and hasattr(self.model, "load_state_dict"):
             self.model.load_state_dict(sd["model"], strict=True)
         for k, v in sd["optimizer"].items():
-            getattr(e, k).copy_(v)
+            dst = getattr(e, k)
+            if k in ("phi_m", "phi_u") and v.shape[-1] != dst.shape[-1]:  # unpadded [r][n] (gathered / re-sharded checkpoints)
+                dst.zero_()
+                dst[:, :e.n].copy_(v)
+            else:
+                dst.copy_(v)
         e.step_dev.fill_(int(sd["step"]))
         e.P.zero_()
         e.P[:, :e.n].copy_(sd["pod_modes"])

@@ -96,6 +96,15 @@ int desmo_build_w(const desmo_shape* s, const float* gates, float* rows, const f
 int desmo_fused_residual_grad(const desmo_shape* s, const float* U, const float* P, const float* phi, const float* omega,
                               const float* W, float* dphi, float* red, void* workspace, void* stream);
 
+/* The same pass in two halves, for multi-GPU steps that overlap the exchange with compute: after _begin returns (stream-ordered) the E
+ * part of red, red[0 .. Kp*mld), is final for this rank and can be all-reduced on a side stream while _finish runs the chain rule and
+ * writes dphi and the scalar tail of red ([sum r^2 | Phi^T Phi | d omega], all-reduced afterwards -- 1 + r*r + 3r floats).  On the
+ * paths that have no such split (FFMA, GEMM) _begin does the whole pass and _finish is a no-op.  Same arguments as above. */
+int desmo_fused_residual_grad_begin(const desmo_shape* s, const float* U, const float* P, const float* phi, const float* omega,
+                                    const float* W, float* dphi, float* red, void* workspace, void* stream);
+int desmo_fused_residual_grad_finish(const desmo_shape* s, const float* U, const float* P, const float* phi, const float* omega,
+                                     const float* W, float* dphi, float* red, void* workspace, void* stream);
+
 /* Backward of forward()'s reconstruction for an ARBITRARY upstream gradient (what autograd runs when the reference loop does
  * `recon, _, _ = model(snapshot); loss = criterion(recon, snapshot); total_loss.backward()`, CYL:711,722,766): grad_recon[m][ld]
  * = dL/drecon in the layout of U (pad columns zero).  Same kernels and outputs as desmo_fused_residual_grad with R := (n_global *

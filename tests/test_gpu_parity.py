@@ -644,3 +644,30 @@ def test_greedy_removal_sweep_matches_oracle(path):
         assert abs(g[1] - w[1]) < 1e-4 * max(w[1], 1e-3), (g, w)
     assert abs(got[-1][1] - 1.0) < 1e-6  # everything removed: recon = 0
     assert rel(model.engine.gates.cpu().numpy(), prm.gates) == 0.0  # gates restored
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_split_pass_equals_monolithic(path):
+    """desmo_fused_residual_grad_begin / _finish (the halves a multi-GPU step interleaves with its two all-reduces) leave exactly what the
+    monolithic call leaves: E is final after _begin, dphi and the scalar tail after _finish."""
+    import ctypes as C
+
+    from desmo_b200 import _lib
+
+    _, modes, snap, prm = make_case("channel", 1500, 120, 4, 2)
+    e = _engine(prm, modes, snap, path)
+    e.build_w(False)
+    e.fused_residual_grad()
+    torch.cuda.synchronize()
+    want_red, want_dphi = e.red.clone(), e.dphi.clone()
+    ecount = e.Kp * e.mld
+    e.red.fill_(7.0)
+    e.dphi.fill_(7.0)
+    args = (C.byref(e.shape), e.U.data_ptr(), e.P.data_ptr(), e.phi.data_ptr(), e.omega.data_ptr(), e.W.data_ptr(), e.dphi.data_ptr(),
+            e.red.data_ptr(), e.workspace.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(e.lib.desmo_fused_residual_grad_begin(*args), "begin")
+    torch.cuda.synchronize()
+    assert torch.equal(e.red[:ecount], want_red[:ecount])
+    _lib.check(e.lib.desmo_fused_residual_grad_finish(*args), "finish")
+    torch.cuda.synchronize()
+    assert torch.equal(e.red, want_red) and torch.equal(e.dphi, want_dphi)
