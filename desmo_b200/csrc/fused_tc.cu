@@ -1,21 +1,22 @@
 // Fused residual + gradient pass on the 5th-gen tensor cores (DESMO_PATH_TC): tcgen05.mma kind::f16 with every fp32 operand
-// split into three bf16 terms (x = x1 + x2 + x3 carries all 24 significand bits; the six products with i + j <= 4 are kept, so
-// each GEMM is accurate to ~2^-24 relative, i.e. fp32-class, at the cost of 6 bf16 MMAs = 3 TF32-equivalents).
+// split into bf16 terms (x = x1 + x2 + x3 carries all 24 significand bits; Rec = G W keeps the six products with i + j <= 4, so it
+// is accurate to ~2^-24 relative, i.e. fp32-class, at the cost of 6 bf16 MMAs = 3 TF32-equivalents).
 //
 // One persistent CTA per SM; a CTA owns tiles of 128 mesh points and walks all snapshots in slabs of 128:
-//   G1  Rec[p x t]    = G[p x lib] W[lib x t]           -> TMEM cols [0,128)   (A = G planes resident in TMEM)   (CYL:548,565-572)
-//   epi r = Rec - U   (U read once from HBM through per-quarter TMA stages: U_STAGES boxes of U_ROWS snapshots x 128 points, any
-//       remaining snapshots of the quarter by register-prefetched loads; R never leaves the SM) (CYL:722); sum r^2;
-//       r -> NPR (= 2) bf16 planes (formed in registers before R_s is free), then R_s[p rows][t contiguous] in shared memory
+//   G1  Rec[p x t]    = G[p x lib] W[lib x t]           -> TMEM cols [0,128)   (A = the three G planes resident in TMEM)  (CYL:548,565-572)
+//   epi r = Rec - U   (U read once from HBM through per-quarter TMA stages; R never leaves the SM) (CYL:722); sum r^2;
+//       r -> two bf16 planes (formed in registers before R_s is free), then R_s[p rows][t contiguous] in shared memory
 //       (128B-swizzled: K-major operand of G3 AND MN-major operand of G4)
-//   G3  D[p x lib]   += R[p x t] W^T[t x lib]           -> TMEM cols [128,128+32*NPR): N-stacked blocks, accumulated over the slabs
+//   G3  D[p x lib]   += R[p x t] W^T[t x lib]           -> TMEM cols [128,192): two N-stacked blocks, accumulated over the slabs
 //   G4  E^T[t x lib] += R^T[t x p] G[p x lib]           -> TMEM cols [256+32*slab, +32), accumulated over the tiles of the CTA and
 //       drained every 32 tiles into the CTA's fp32 partial (the tensor core truncates when it adds into the accumulator)
-// Warp roles (20 warps): warp 0 = TMA producer (W slab planes), warp 1 = MMA issuer (one elected thread), warps 2-3 = TMA
-// producers of U (warp 2 also allocates TMEM), warps 4..19 = epilogue: thread <-> (mesh point == TMEM lane, snapshot quarter h);
+// Warp roles (20 warps): warp 0 = TMA producer (W slab planes, phi / P tiles), warp 1 = MMA issuer (one elected thread), warps 2-3 =
+// TMA producers of U (warp 2 also allocates TMEM), warps 4..19 = epilogue: thread <-> (mesh point == TMEM lane, snapshot quarter h);
 // warp e = 4 + 4h + q handles lane quadrant q and snapshots 32h..32h+31 of the slab.
-// The MMA issuer runs G1 of slab s+1 ahead of G3/G4 of slab s, so the tensor pipe works while the epilogue forms R; G4 releases
-// R_s lane quadrant by lane quadrant; the library row of the next tile is evaluated under the last slab's MMAs.
+// The MMA issuer always runs G1 of the next slab-tile ahead of G3/G4 of the current one -- across tile boundaries too: the library
+// row of the NEXT tile is evaluated one term per slab in the epilogue's slack (phi / P arrive by TMA a tile ahead), its TMEM planes
+// (A of G1) are written as soon as G1 of the current tile's last slab has completed, and its shared-memory planes (B of G4) are
+// written lane quadrant by lane quadrant together with the first R_s of the new tile, when G4 has released that quadrant.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -38,6 +39,7 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = 128 + EPI_THREADS;
 constexpr int NQ = 4;              // snapshot quarters per slab
 constexpr int QT = BT / NQ;        // 32 snapshots per epilogue thread
+constexpr int TPT = KP / NQ;       // library terms evaluated per epilogue thread (the four quarters of a point share the row)
 constexpr uint32_t R_PLANE = 2 * BP * 128;            // one bf16 plane of R: 2 boxes [128 p rows x 128 B (64 t)]
 constexpr uint32_t W_BOX = 3 * KP * 128;              // W slab box: [3 planes x 32 lib rows][128 B = 64 t]; planes stacked along rows
 constexpr uint32_t W_PLANE = KP * 128;                // row offset of a plane inside a box
@@ -46,52 +48,37 @@ constexpr uint32_t G_PLANE = 2 * KP * 128;            // one bf16 plane of G: 2 
 // Planes of R (and of the W / G operands that multiply it) used by the two gradient GEMMs G3 / G4.  Two bf16 planes carry 16
 // significand bits; with the three products R1*X1 + R1*X2 + R2*X1 the gradients come out at ~3e-7 relative (measured against an
 // fp64 evaluation on the golden cases: 2e-7 .. 1.4e-6, the same class as a plain fp32 GEMM), far inside the 1e-5 gate, while Rec = G W
-// keeps all three planes (R is a small difference of large numbers).  DESMO_NPR=3 restores the six-product gradients.
-#ifndef DESMO_NPR
-#define DESMO_NPR 2
-#endif
-constexpr int NPR = DESMO_NPR;
-static_assert(NPR == 2 || NPR == 3, "R planes");
+// keeps all three planes (R is a small difference of large numbers).
+constexpr int NPR = 2;
 constexpr uint32_t R_OFF = 0;
 constexpr uint32_t W_OFF = R_OFF + NPR * R_PLANE;
-constexpr uint32_t G_OFF = W_OFF + 2 * W_SLAB;
-// U staging: each snapshot quarter of the epilogue owns a private ring of 3 TMA stages of [8 snapshots][128 points] fp32.
+constexpr uint32_t G_OFF = W_OFF + 2 * W_SLAB;        // two planes (B of G4); G1 reads its three planes from TMEM
+constexpr uint32_t LAT_OFF = G_OFF + 2 * G_PLANE;     // phi tile [kMaxR][128] then P tile [kMaxR][128] of the tile whose library is next
+constexpr uint32_t LAT_HALF = kMaxR * BP * 4;
+// U staging: each snapshot quarter of the epilogue owns a private ring of U_RING TMA stages of [U_ROWS snapshots][128 points] fp32.
 // Private rings matter: mbarrier parity waits are only sound if a waiter is never two phases away from the barrier, which a
 // ring shared by independently progressing consumer groups cannot guarantee.
-constexpr uint32_t U_OFF = G_OFF + 3 * G_PLANE;
-// One [32 snapshots][128 points] box (16 KB) per quarter and slab-tile: a single TMA instruction, a single FULL / EMPTY hand-over and
-// no register-prefetched tail.  Measured equal to or ~1 % faster than three 8-row stages + 8 tail loads (profiles/README.md), with 40
-// fewer instructions per thread and slab.
+constexpr uint32_t U_OFF = LAT_OFF + 2 * LAT_HALF;
 #ifndef DESMO_U_ROWS
 #define DESMO_U_ROWS 32
 #endif
-constexpr int U_ROWS = DESMO_U_ROWS;  // snapshots per TMA stage
-constexpr uint32_t U_STAGE = U_ROWS * BP * 4;          // 4096 (must be a multiple of 128 B, the TMA destination alignment)
-#ifndef DESMO_U_STAGES
-#define DESMO_U_STAGES 1
+constexpr int U_ROWS = DESMO_U_ROWS;                   // snapshots per TMA stage
+constexpr int U_PER = QT / U_ROWS;                     // stages a quarter consumes per slab-tile
+#ifndef DESMO_U_RING
+#define DESMO_U_RING 1
 #endif
-constexpr int U_STAGES = DESMO_U_STAGES;               // per quarter
-constexpr int U_TAIL = QT - U_STAGES * U_ROWS;         // snapshots of a quarter fetched by the epilogue threads themselves (registers)
-// Experiment hook: TMA L2-prefetches of U issued by the producer threads U_PREFETCH slab-tiles ahead of the ring.  Measured (round 2,
-// profiles/README.md): 5200 -> 5650-6170 cycles per slab-tile for distances 1-4, i.e. slower -- the prefetches queue in the same TMA
-// unit as the ring's loads -- so the default is off.
-#ifndef DESMO_U_PREFETCH
-#define DESMO_U_PREFETCH 0
-#endif
-constexpr int U_PREFETCH = DESMO_U_PREFETCH;
-constexpr uint32_t RED_OFF = U_OFF + NQ * U_STAGES * U_STAGE;  // (4 quadrants x kScal doubles)
-constexpr uint32_t SMEM_BYTES = RED_OFF + 4 * kScal * 8 + 1024;  // + alignment slack
-static_assert(SMEM_BYTES + 1024 <= 232448, "dynamic + static shared memory must fit the 227 KB of an sm_100 CTA");
-static_assert(U_TAIL >= 0 && U_STAGE % 128 == 0, "U stage shape");
-constexpr uint32_t TMEM_REC = 0, TMEM_D = 128, TMEM_E = 256;  // D: NPR column blocks of 32 (N-stacked B planes), summed in the epilogue
-// G1's A operand (the three bf16 planes of the library tile, [point = lane][lib pair = column], 16 columns per plane) can live in
+constexpr int U_RING = DESMO_U_RING;                   // stages in a quarter's ring
+constexpr uint32_t U_STAGE = U_ROWS * BP * 4;          // must be a multiple of 128 B, the TMA destination alignment
+constexpr uint32_t TRACE_OFF = U_OFF + NQ * U_RING * U_STAGE;  // debug builds only: 6 event logs of TRACE_LEN entries
+constexpr int TRACE_LEN = 384;
+constexpr uint32_t SMEM_BYTES = TRACE_OFF + 1024;  // + alignment slack
+constexpr uint32_t SMEM_BYTES_DEBUG = SMEM_BYTES + 6 * TRACE_LEN * 8;
+static_assert(SMEM_BYTES + 2048 <= 232448, "dynamic + static shared memory must fit the 227 KB of an sm_100 CTA");
+static_assert(QT % U_ROWS == 0 && U_STAGE % 128 == 0 && U_RING >= U_PER, "U stage shape");
+constexpr uint32_t TMEM_REC = 0, TMEM_D = 128, TMEM_G = 192, TMEM_E = 256;  // D: NPR column blocks of 32 (N-stacked B planes), summed in the epilogue
+// G1's A operand (the three bf16 planes of the library tile, [point = lane][lib pair = column], 16 columns per plane) lives in
 // TMEM: an SS-mode MMA re-reads its 4 KB A tile from shared memory for every instruction, and shared-memory bandwidth is what
-// binds this kernel (ncu: tensor-core operand reads + LSU ~ 96 % of the data pipe).  Needs NPR == 2 (D then ends at column 192).
-#ifndef DESMO_G1_TMEM
-#define DESMO_G1_TMEM 1
-#endif
-constexpr bool G1_TMEM = DESMO_G1_TMEM && NPR == 2;
-constexpr uint32_t TMEM_G = 192;
+// binds this kernel (ncu: tensor-core operand reads + LSU ~ 80-96 % of the data pipe).
 }  // namespace tc
 
 struct TcArgs {
@@ -150,8 +137,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking probe
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred q;\n\tmbarrier.test_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -208,15 +198,8 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// x = b1 + b2 + b3 (bf16 each, round-to-nearest): packs two consecutive elements (lo = first) per 32-bit word
+// x ~ b1 + b2 (bf16 each, round-to-nearest): packs two consecutive elements (lo = first) per 32-bit word
 // (the conversions are `volatile` so that the compiler cannot sink them below the mbarrier wait that follows them in the epilogue)
-__device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
-    asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w1) : "f"(x1), "f"(x0));
-    const float e0 = x0 - __uint_as_float(w1 << 16), e1 = x1 - __uint_as_float(w1 & 0xffff0000u);
-    asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w2) : "f"(e1), "f"(e0));
-    const float f0 = e0 - __uint_as_float(w2 << 16), f1 = e1 - __uint_as_float(w2 & 0xffff0000u);
-    asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w3) : "f"(f1), "f"(f0));
-}
 __device__ __forceinline__ void split2_pair(float x0, float x1, uint32_t& w1, uint32_t& w2) {
     asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w1) : "f"(x1), "f"(x0));
     const float e0 = x0 - __uint_as_float(w1 << 16), e1 = x1 - __uint_as_float(w1 & 0xffff0000u);
@@ -227,11 +210,7 @@ __device__ __forceinline__ void split2_pair(float x0, float x1, uint32_t& w1, ui
 // Descriptors: the high word is constant per operand role; the low word is (addr >> 4) | (LBO >> 4) << 16, so stepping through
 // planes / k-steps is ONE 32-bit add of a compile-time constant per operand (smem addresses < 256 KB never carry out of 14 bits).
 #define DESMO_PAIRS(X) X(2, 0) X(0, 2) X(1, 1) X(1, 0) X(0, 1) X(0, 0)
-#if DESMO_NPR == 3
-#define DESMO_GRAD_PAIRS(X) DESMO_PAIRS(X)
-#else
 #define DESMO_GRAD_PAIRS(X) X(1, 0) X(0, 1) X(0, 0)
-#endif
 __device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
 
@@ -240,22 +219,33 @@ constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1
 template <bool kDebug, bool kSupplied>
 __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmW,
                                                                           const __grid_constant__ CUtensorMap tmU,
-                                                                          const __grid_constant__ CUtensorMap tmUp) {
+                                                                          const __grid_constant__ CUtensorMap tmPhi,
+                                                                          const __grid_constant__ CUtensorMap tmP) {
     using namespace tc;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[12 + 2 * tc::NQ * tc::U_STAGES + 4];
+    enum { W_FULL0 = 0, W_FULL1, W_EMPTY0, W_EMPTY1, REC_FULL, REC_EMPTY, R_FULL, GT_FULL, LAT_FULL, LAT_EMPTY, D_FULL, D_EMPTY,
+           R_EMPTYQ0, U_FULL0 = R_EMPTYQ0 + 4, U_EMPTY0 = U_FULL0 + NQ * U_RING, NBARS = U_EMPTY0 + NQ * U_RING };
+    __shared__ __align__(8) uint64_t bars[NBARS];
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t sink_s[32];  // write-only (see the epilogue)
     __shared__ float omega_s[3 * kMaxR];
+    __shared__ uint32_t desc_s[KP];  // packed description of library term j: kind | deg << 3 | mode indices (3 bits each) << 6
+    __shared__ double red_s[4];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
-    double* red_s = reinterpret_cast<double*>(smem + RED_OFF);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    enum { W_FULL0 = 0, W_FULL1, W_EMPTY0, W_EMPTY1, REC_FULL, REC_EMPTY, R_FULL, R_EMPTY, G_FULL, G_EMPTY, D_FULL, D_EMPTY,
-           U_FULL0, U_EMPTY0 = U_FULL0 + NQ * U_STAGES, R_EMPTYQ0 = U_EMPTY0 + NQ * U_STAGES };
+    if (kDebug) for (int i = tid; i < 6 * TRACE_LEN; i += THREADS) reinterpret_cast<unsigned long long*>(smem + TRACE_OFF)[i] = 0ull;
     auto bar = [&](int i) { return smem_u32(&bars[i]); };
     auto mbar_wait = [&](uint32_t b, uint32_t parity, int tag = 0, int iter = 0) { mbar_wait_t<kDebug>(b, parity, tag, iter); };
     auto now = [&]() -> long long { return kDebug ? clock64() : 0ll; };
+    // debug timeline of CTA 0 (tools/tc_timeline.py): per-role logs of (tag, iteration, clock) for a window of slab-tiles
+    // (kept in shared memory behind the U rings and copied out at the end: a store to mapped host memory per event would stall the roles)
+    int trc = 0;
+    unsigned long long* trace_s = reinterpret_cast<unsigned long long*>(smem + TRACE_OFF);
+    auto trace = [&](int log, int tag, int it_) {
+        if (kDebug && blockIdx.x == 0 && a.dbg && it_ >= 24 && it_ < 48 && trc < TRACE_LEN)
+            trace_s[log * TRACE_LEN + trc++] = ((unsigned long long)tag << 56) | ((unsigned long long)it_ << 40) | (clock64() & 0xffffffffffull);
+    };
 
     const int nslab = a.nslab;
     const long long ntiles = a.ld / BP;
@@ -264,9 +254,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
 
     if (tid == 32) {
         mbar_init(bar(W_FULL0), 1); mbar_init(bar(W_FULL1), 1); mbar_init(bar(W_EMPTY0), 1); mbar_init(bar(W_EMPTY1), 1);
-        mbar_init(bar(REC_FULL), 1); mbar_init(bar(REC_EMPTY), EPI_THREADS); mbar_init(bar(R_FULL), EPI_THREADS); mbar_init(bar(R_EMPTY), 1);
-        mbar_init(bar(G_FULL), EPI_THREADS); mbar_init(bar(G_EMPTY), 1); mbar_init(bar(D_FULL), 1); mbar_init(bar(D_EMPTY), EPI_THREADS);
-        for (int i = 0; i < NQ * U_STAGES; ++i) { mbar_init(bar(U_FULL0 + i), 1); mbar_init(bar(U_EMPTY0 + i), 128); }
+        mbar_init(bar(REC_FULL), 1); mbar_init(bar(REC_EMPTY), EPI_THREADS); mbar_init(bar(R_FULL), EPI_THREADS);
+        mbar_init(bar(GT_FULL), EPI_THREADS); mbar_init(bar(LAT_FULL), 1); mbar_init(bar(LAT_EMPTY), EPI_THREADS);
+        mbar_init(bar(D_FULL), 1); mbar_init(bar(D_EMPTY), EPI_THREADS);
+        for (int i = 0; i < NQ * U_RING; ++i) { mbar_init(bar(U_FULL0 + i), 1); mbar_init(bar(U_EMPTY0 + i), 128); }
         for (int i = 0; i < 4; ++i) mbar_init(bar(R_EMPTYQ0 + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -274,68 +265,86 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < 4 * kScal; i += THREADS) red_s[i] = 0.0;
+    if (tid < 4) red_s[tid] = 0.0;
     if (tid < 3 * a.r) omega_s[tid] = a.omega[tid];
+    if (tid >= 64 && tid < 64 + KP) {
+        // term j of the library (CYL:376-434 column order, then the sin / cos / tanh blocks of CYL:565-567)
+        const int j = tid - 64;
+        uint32_t d = 4u;  // padding column: identically zero
+        if (j < a.T) {
+            const int deg = a.mt.deg[j];
+            d = (uint32_t)deg << 3;
+            for (int q = 0; q < deg; ++q) d |= (uint32_t)a.mt.idx[j][q] << (6 + 3 * q);
+        } else if (j < a.K) {
+            const int b = (j - a.T) / a.r, i = (j - a.T) - b * a.r;
+            d = (uint32_t)(1 + b) | ((uint32_t)i << 6);
+        }
+        desc_s[j] = d;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
 
     if (warp == 0) {
-        // ================================================ TMA producer: W slab planes ================================================
+        // ======================== TMA producer: W slab planes; phi / P rows of the tile whose library is evaluated next ========================
         if (elect_one_sync()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmPhi) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
+            int lat_k = 0;  // next tile (CTA-local index) whose phi / P rows are requested; one buffer, released by the epilogue (LAT_EMPTY)
+            auto lat_issue = [&]() {
+                const int x0 = (int)((blockIdx.x + (long long)lat_k * gridDim.x) * BP);
+                mbar_expect_tx(bar(LAT_FULL), 2u * a.r * BP * 4u);
+                tma_load_2d(sbase + LAT_OFF, &tmPhi, x0, 0, bar(LAT_FULL));
+                tma_load_2d(sbase + LAT_OFF + LAT_HALF, &tmP, x0, 0, bar(LAT_FULL));
+                ++lat_k;
+            };
+            if (my_tiles > 0) lat_issue();
             for (int it = 0; it < total; ++it) {
                 const int buf = it & 1, slab = it % nslab;
+                // polled, never waited for here: the W slabs must not queue behind the epilogue's progress through the library
+                if (lat_k < my_tiles && mbar_test(bar(LAT_EMPTY), (lat_k - 1) & 1)) lat_issue();
                 if (it >= 2) mbar_wait(bar(W_EMPTY0 + buf), ((it >> 1) & 1) ^ 1, 1, it);
                 mbar_expect_tx(bar(W_FULL0 + buf), W_SLAB);
                 for (int h = 0; h < 2; ++h)
                     tma_load_2d(sbase + W_OFF + buf * W_SLAB + h * W_BOX, &tmW, slab * BT + h * 64, 0, bar(W_FULL0 + buf));
             }
+            while (lat_k < my_tiles) {
+                mbar_wait(bar(LAT_EMPTY), (lat_k - 1) & 1, 13, lat_k);
+                lat_issue();
+            }
         }
     } else if (warp == 3 || warp == 2) {
-        // ================= TMA producers: U boxes [U_ROWS snapshots][128 points]; each thread feeds the private stages of two quarters ======
-        // The stages of a quarter hold exactly one slab-tile, so the boxes of the NEXT slab-tile are requested as soon as the current ones
-        // are consumed; snapshots beyond U_STAGES * U_ROWS (none by default) are fetched by the epilogue threads themselves one slab ahead.
-        // No divisions in the loop: one thread sustains ~1 TMA instruction per 400 cycles.
+        // ================= TMA producers: U boxes [U_ROWS snapshots][128 points]; each thread feeds the private rings of two quarters ======
+        // A quarter consumes U_PER stages per slab-tile; the box of a stage is requested as soon as the stage's previous contents are
+        // consumed.  No divisions in the loop: one thread sustains ~1 TMA instruction per 400 cycles.
         if (elect_one_sync()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmU) : "memory");
             const int h0 = (warp - 2) * 2;
-            int slab = 0;
-            uint32_t par = 1;
+            int slab = 0, st = 0, use = 0;  // ring position and how often the ring has wrapped
             long long tile = blockIdx.x;
             unsigned long long tp0 = 0;
             const long long tps = now();
-            // L2 prefetch cursor, U_PREFETCH slab-tiles ahead of the ring (one [32 snapshots][128 points] box per quarter)
-            int pslab = 0, pit = 0;
-            long long ptile = blockIdx.x;
-            auto prefetch_next = [&]() {
-                if (U_PREFETCH == 0 || pit >= total) return;
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) tma_prefetch_2d(&tmUp, (int)(ptile * BP), pslab * BT + (h0 + hh) * QT);
-                ++pit;
-                if (++pslab == nslab) { pslab = 0; ptile += gridDim.x; }
-            };
-            if (U_PREFETCH > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmUp) : "memory");
-            for (int i = 0; i < U_PREFETCH; ++i) prefetch_next();
             for (int it = 0; it < total; ++it) {
-                prefetch_next();
 #pragma unroll
-                for (int k = 0; k < U_STAGES; ++k)
+                for (int k = 0; k < U_PER; ++k) {
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
-                        const int st = (h0 + hh) * U_STAGES + k;
+                        const int b = (h0 + hh) * U_RING + st;
                         long long cp0 = now();
-                        if (it > 0) mbar_wait(bar(U_EMPTY0 + st), par, 2, it);
+                        if (use > 0) mbar_wait(bar(U_EMPTY0 + b), (use - 1) & 1, 2, it);
                         tp0 += now() - cp0;
+                        if (warp == 2) trace(5, 40 + hh, it);
 #ifdef EXP_NO_UTMA
-                        mbar_arrive(bar(U_FULL0 + st));
+                        mbar_arrive(bar(U_FULL0 + b));
 #else
-                        mbar_expect_tx(bar(U_FULL0 + st), U_STAGE);
-                        tma_load_2d(sbase + U_OFF + st * U_STAGE, &tmU, (int)(tile * BP), slab * BT + (h0 + hh) * QT + k * U_ROWS, bar(U_FULL0 + st));
+                        mbar_expect_tx(bar(U_FULL0 + b), U_STAGE);
+                        tma_load_2d(sbase + U_OFF + b * U_STAGE, &tmU, (int)(tile * BP), slab * BT + (h0 + hh) * QT + k * U_ROWS, bar(U_FULL0 + b));
 #endif
                     }
-                par ^= 1;
+                    if (++st == U_RING) { st = 0; ++use; }
+                }
                 if (++slab == nslab) { slab = 0; tile += gridDim.x; }
             }
             if (a.dbg) { a.dbg[blockIdx.x * 32 + 20 + (warp - 2) * 2] = tp0; a.dbg[blockIdx.x * 32 + 21 + (warp - 2) * 2] = now() - tps; }
@@ -343,32 +352,30 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
     } else if (warp == 1) {
         // ================================================ MMA issuer ================================================
         if (elect_one_sync()) {
-            constexpr uint32_t idesc_g1 = make_idesc_bf16(BP, BT, 1, 1);
-            constexpr uint32_t idesc_g1_ts = make_idesc_bf16(BP, BT, 0, 1);  // A from TMEM: rows = lanes, K along columns
+            constexpr uint32_t idesc_g1 = make_idesc_bf16(BP, BT, 0, 1);  // A from TMEM: rows = lanes, K along columns; B = W_s MN-major
             constexpr uint32_t idesc_g4 = make_idesc_bf16(BT, KP, 1, 0);
             unsigned long long tm[6] = {0, 0, 0, 0, 0, 0};
             auto issue_g1 = [&](int it) {
                 const int buf = it & 1, slab = it % nslab, tl = it / nslab;
                 long long c0 = now();
+                trace(0, 1, it);
                 mbar_wait(bar(W_FULL0 + buf), (it >> 1) & 1, 3, it);
                 long long c1 = now(); tm[0] += c1 - c0;
+                trace(0, 2, it);
                 if (it > 0) mbar_wait(bar(REC_EMPTY), (it - 1) & 1, 4, it);
                 c0 = now(); tm[1] += c0 - c1;
-                if (slab == 0) mbar_wait(bar(G_FULL), tl & 1, 5, it);
+                trace(0, 3, it);
+                if (slab == 0) mbar_wait(bar(GT_FULL), tl & 1, 5, it);
                 c1 = now(); tm[2] += c1 - c0;
+                trace(0, 4, it);
                 tc_fence_after();
-                // A = G_s MN-major (M = points, 2 boxes LBO = 4096), B = W_s MN-major (N = snapshots, 2 boxes LBO = W_BOX)
-                const uint32_t ga_lo = ((sbase + G_OFF) >> 4) | ((KP * 128u >> 4) << 16);
+                // A = library planes in TMEM (16 columns per plane, 8 per k-step), B = W_s MN-major (N = snapshots, 2 boxes LBO = W_BOX)
                 const uint32_t wa_lo = ((sbase + W_OFF + buf * W_SLAB) >> 4) | ((W_BOX >> 4) << 16);
                 uint32_t acc = 0;
 #define G1_PAIR(PA, PB)                                                                                              \
     _Pragma("unroll") for (int ks = 0; ks < KP / 16; ++ks) {                                                          \
-        if (G1_TMEM)                                                                                                  \
-            mma_bf16_ts(tmem + TMEM_REC, tmem + TMEM_G + PA * (KP / 2) + ks * 8,                                      \
-                        desc_from(wa_lo + ((PB * W_PLANE + ks * 2048) >> 4), kDescHi), idesc_g1_ts, acc);             \
-        else                                                                                                          \
-            mma_bf16(tmem + TMEM_REC, desc_from(ga_lo + ((PA * G_PLANE + ks * 2048) >> 4), kDescHi),                  \
-                     desc_from(wa_lo + ((PB * W_PLANE + ks * 2048) >> 4), kDescHi), idesc_g1, acc);                   \
+        mma_bf16_ts(tmem + TMEM_REC, tmem + TMEM_G + PA * (KP / 2) + ks * 8,                                          \
+                    desc_from(wa_lo + ((PB * W_PLANE + ks * 2048) >> 4), kDescHi), idesc_g1, acc);                     \
         acc = 1;                                                                                                      \
     }
 #ifndef EXP_NO_G1
@@ -376,12 +383,15 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
 #endif
 #undef G1_PAIR
                 umma_commit(bar(REC_FULL));
+                trace(0, 5, it);
             };
             auto issue_g34 = [&](int it) {
                 const int buf = it & 1, slab = it % nslab, tl = it / nslab;
                 long long c0 = now();
+                trace(0, 6, it);
                 mbar_wait(bar(R_FULL), it & 1, 6, it);
                 long long c1 = now(); tm[3] += c1 - c0;
+                trace(0, 7, it);
                 if (slab == 0 && tl > 0) mbar_wait(bar(D_EMPTY), (tl - 1) & 1, 7, it);
                 c0 = now(); tm[4] += c0 - c1;
                 tc_fence_after();
@@ -390,8 +400,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 const uint32_t wk_lo = ((sbase + W_OFF + buf * W_SLAB) >> 4) | (1u << 16);        // W_s K-major (G3 B)
                 const uint32_t gk_lo = ((sbase + G_OFF) >> 4) | (1u << 16);                       // G_s K-major (G4 B)
                 // G3: D += R W^T   (K = snapshots: 8 k-steps of 16; box = ks / 4, 32 B per k-step inside the swizzled row).
-                // The B planes are stacked along N: plane a of R multiplies planes 0..2-a of W in ONE MMA of N = 32*(3-a); column
-                // block b of D then holds sum_a R_a W_b and the three blocks are added when D is read (A is fetched 3x, not 6x).
+                // The B planes are stacked along N: plane a of R multiplies planes 0..1-a of W in ONE MMA of N = 32*(2-a); column
+                // block b of D then holds sum_a R_a W_b and the blocks are added when D is read (A is fetched 2x, not 3x).
                 uint32_t acc0 = slab > 0 ? 1u : 0u;
 #define G3_PLANE(PA)                                                                                                 \
     _Pragma("unroll") for (int ks = 0; ks < BT / 16; ++ks) {                                                          \
@@ -402,18 +412,16 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
     }
 #ifndef EXP_NO_G3
                 G3_PLANE(0) G3_PLANE(1)
-#if DESMO_NPR == 3
-                G3_PLANE(2)
-#endif
 #endif
 #undef G3_PLANE
                 umma_commit(bar(W_EMPTY0 + buf));  // W slab is dead after G3: let the producer refill it while G4 runs
+                trace(0, 9, it);
                 uint32_t acc = (tl % E_FLUSH_TILES) > 0 ? 1u : 0u;  // fresh E accumulators after every flush
                 const uint32_t e_tmem = tmem + TMEM_E + slab * KP;
                 // G4: E^T += R^T G  (K = points: 8 k-steps of 16 rows = 2048 B; B = G_s K-major, box = ks / 4).  Issued lane quadrant
-                // by lane quadrant (k-steps 2q, 2q+1 read the R_s rows of points 32q..32q+31 only) with one commit each: the epilogue
-                // warps of quadrant q may overwrite their rows of R_s while G4 still works on the later quadrants, so only the LAST
-                // quadrant's stores (a quarter of the volume) are serialised between G4 of this slab and G3 of the next.
+                // by lane quadrant (k-steps 2q, 2q+1 read the R_s rows and G_s columns of points 32q..32q+31 only) with one commit each:
+                // the epilogue warps of quadrant q may overwrite their part of R_s (and, at a tile boundary, of G_s) while G4 still
+                // works on the later quadrants, so only the LAST quadrant's stores are serialised between G4 of this slab and G3 of the next.
 #define G4_PAIR(PA, PB)                                                                                              \
     _Pragma("unroll") for (int kk = 0; kk < 2; ++kk) {                                                                \
         const int ks = 2 * qq + kk;                                                                                   \
@@ -427,19 +435,16 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                     DESMO_GRAD_PAIRS(G4_PAIR)
 #endif
                     umma_commit(bar(R_EMPTYQ0 + qq));
+                    trace(0, 10 + qq, it);
                 }
 #undef G4_PAIR
-                if (slab == nslab - 1) {
-                    umma_commit(bar(D_FULL));
-                    umma_commit(bar(G_EMPTY));
-                }
+                if (slab == nslab - 1) umma_commit(bar(D_FULL));
             };
             if (total > 0) issue_g1(0);
             for (int it = 0; it < total; ++it) {
-                const bool next_same_tile = (it + 1 < total) && ((it + 1) % nslab != 0);
-                if (next_same_tile) issue_g1(it + 1);  // run ahead: the tensor pipe works on G1(s+1) while the epilogue forms R(s)
+                // run ahead, across tile boundaries too: the tensor pipe works on G1 of the next slab-tile while the epilogue forms R
+                if (it + 1 < total) issue_g1(it + 1);
                 issue_g34(it);
-                if (!next_same_tile && it + 1 < total) issue_g1(it + 1);  // new tile: its G needs G4 of the old tile finished
             }
             if (a.dbg) for (int i = 0; i < 5; ++i) a.dbg[blockIdx.x * 32 + i] = tm[i];
         }
@@ -447,28 +452,23 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         // ================================================ epilogue warps ================================================
         // thread <-> (mesh point p == TMEM lane, quarter h of the slab's snapshots): 16 warps, q = lane quadrant, h = snapshots 32h..32h+31
         const int e = warp - 4, q = e & 3, h = e >> 2;
+        const int elog = (lane == 0 && (e == 0 || e == 5 || e == 10 || e == 15)) ? 1 + e / 5 : -1;
+        auto etrace = [&](int tag, int it_) { if (kDebug && elog >= 0) trace(elog, tag, it_); };
         const int p = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         double loss_acc = 0.0;
-        float lat[kMaxR];
         unsigned long long te[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const long long tstart = now();
 
         auto store_d = [&](int tile_local, long long tile) {
-            // D = R W^T of the finished tile: quarter h drains library columns 8h..8h+7 (three N-stacked blocks summed) to Dacc[j][x];
+            // D = R W^T of the finished tile: quarter h drains library columns 8h..8h+7 (the N-stacked blocks summed) to Dacc[j][x];
             // the chain rule through POOL_DATA / sin / cos / tanh runs in a separate light kernel, off this kernel's critical path.
             const long long x = tile * BP + p;
             mbar_wait(bar(D_FULL), tile_local & 1, 8, tile_local);
             tc_fence_after();
-            uint32_t v0[8], v1[8], v2[8];
+            uint32_t v0[8], v1[8];
             tmem_ld8(tmem + lane_addr + TMEM_D + h * 8, v0);
             tmem_ld8(tmem + lane_addr + TMEM_D + KP + h * 8, v1);
-            if (NPR == 3) {
-                tmem_ld8(tmem + lane_addr + TMEM_D + 2 * KP + h * 8, v2);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v2[j] = 0u;
-            }
             tmem_ld_wait();
             if ((tile_local + 1) % E_FLUSH_TILES == 0 || tile_local == my_tiles - 1) {
                 // E^T accumulators -> this CTA's fp32 partial (round-to-nearest adds), then the MMA issuer restarts them at zero
@@ -499,132 +499,143 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 if (h * 8 + j < a.K)  // rows K..Kp-1 of D belong to zero rows of W: never read by the chain rule
-                    a.Dacc[(long long)(h * 8 + j) * a.ld + x] = (__uint_as_float(v2[j]) + __uint_as_float(v1[j])) + __uint_as_float(v0[j]);
+                    a.Dacc[(long long)(h * 8 + j) * a.ld + x] = __uint_as_float(v1[j]) + __uint_as_float(v0[j]);
             // the accumulator is handed back only after the loaded registers were consumed: an experiment that arrived on REC_EMPTY
             // straight after tcgen05.wait::ld (before using the data) produced wrong residuals in a few columns (profiles/README.md)
             tc_fence_before();
             mbar_arrive(bar(D_EMPTY));
         };
 
-        // ---- library row of a point (CYL:538-548,565-567).  The four quarters share the work (quarter h takes library terms
-        //      j = h, h+4, ...).  eval_library(next tile) runs while G3/G4 of the current tile's last slab occupy the tensor pipe,
-        //      so only the split + 24 two-byte stores sit between "G_s free" and "G_s full" at a tile boundary.  Rolled loops on
-        //      purpose (gv[] lives in local memory): this runs once per tile and straight-line code only thrashes the I-cache. ----
-        float gv[KP / NQ];
+        // ---- library row of a point (CYL:538-548,565-567).  The four quarters share the work: quarter h owns the library PAIRS
+        //      c = h, h+4, h+8, h+12 (terms 2c, 2c+1) -- a pair is one packed word of the TMEM-resident A operand of G1, and the
+        //      interleave spreads the sin / cos / tanh terms (the last 3r of K) over the quarters.  The row of the NEXT tile is
+        //      evaluated term by term in the slack after each slab's R_FULL hand-over, from the phi / P rows the producer staged in
+        //      shared memory; gv[tile parity][.] keeps the fp32 terms until both operand copies (TMEM, G_s) are written. ----
+        const float* phi_s = reinterpret_cast<const float*>(smem + LAT_OFF);
+        const float* P_s = reinterpret_cast<const float*>(smem + LAT_OFF + LAT_HALF);
+        float gv[2][TPT];
         unsigned long long tl2[2] = {0, 0};
-        // quarter h owns the library PAIRS c = h, h+4, h+8, h+12 (terms 2c, 2c+1): a pair is one packed word of the TMEM-resident A
-        // operand of G1, and the interleave spreads the sin / cos / tanh terms (the last 3r of K) over the four quarters
         auto term_of = [&](int jj) { return 2 * (h + (jj >> 1) * NQ) + (jj & 1); };
-        auto eval_library = [&](long long tile_) {
-            const long long x_ = tile_ * BP + p;
+        auto eval_term = [&](int jj) -> float {
+            const uint32_t d = desc_s[term_of(jj)];
+            const uint32_t kind = d & 7u;
+#ifdef EXP_NO_EVAL
+            return 0.25f + (float)kind;
+#endif
+            if (kind == 4u) return 0.0f;
+            if (kind == 0u) {  // monomial: left-to-right product of the latent modes, as CYL:390-431
+                const int deg = (d >> 3) & 7;
+                float v = 1.0f;
+                for (int k = 0; k < deg; ++k) {
+                    const int i = (d >> (6 + 3 * k)) & 7;
+                    const float f = phi_s[i * BP + p] * P_s[i * BP + p];
+                    v = (k == 0) ? f : v * f;
+                }
+                return v;
+            }
+            const int i = (d >> 6) & 7;
+            const float arg = omega_s[3 * i + (int)kind - 1] * (phi_s[i * BP + p] * P_s[i * BP + p]);
+#ifdef EXP_NO_TRIG
+            return arg;
+#endif
+            return (kind == 1u) ? sinf(arg) : (kind == 2u) ? cosf(arg) : tanhf(arg);
+        };
+        int ev_next = 0;       // terms of the next library row evaluated so far
+        int ev_tile = 0;       // CTA-local index of the tile that row belongs to
+        auto eval_upto = [&](int upto) {
+            if (ev_next >= upto) return;
             const long long ce0 = now();
-            for (int i = 0; i < a.r; ++i) lat[i] = a.phi[(long long)i * a.ld + x_] * a.P[(long long)i * a.ld + x_];
+            if (ev_next == 0) mbar_wait(bar(LAT_FULL), ev_tile & 1, 14, ev_tile);
             const long long ce1 = now();
 #pragma unroll 1
-            for (int jj = 0; jj < KP / NQ; ++jj) {
-                const int j = term_of(jj);
-                float v = 0.0f;
-                if (j < a.T) {
-                    v = monomial(a.mt, j, lat, 1);
-                } else if (j < a.K) {
-                    const int b = (j - a.T) / a.r, i = (j - a.T) - b * a.r;
-                    const float arg = omega_s[3 * i + b] * lat[i];
-                    v = (b == 0) ? sinf(arg) : (b == 1) ? cosf(arg) : tanhf(arg);
-                }
-                gv[jj] = v;
-            }
+            for (; ev_next < upto; ++ev_next) gv[ev_tile & 1][ev_next] = eval_term(ev_next);
+            // gv was stored, so the ld.shared of phi_s / P_s have returned: the buffer may be refilled
+            if (ev_next == TPT) mbar_arrive(bar(LAT_EMPTY));
             if (kDebug) { tl2[0] += ce1 - ce0; tl2[1] += now() - ce1; }
         };
-        auto store_library = [&]() {  // bf16 planes: G_s[lib rows][p contiguous] (B of G4; A of G1 unless G1_TMEM) and TMEM [p lane][lib pairs]
+        auto split_term = [&](float v, uint16_t& b1, uint16_t& b2, uint16_t& b3) {
+            const __nv_bfloat16 c1 = __float2bfloat16_rn(v);
+            const float e1 = v - __bfloat162float(c1);
+            const __nv_bfloat16 c2 = __float2bfloat16_rn(e1);
+            const __nv_bfloat16 c3 = __float2bfloat16_rn(e1 - __bfloat162float(c2));
+            b1 = __bfloat16_as_ushort(c1); b2 = __bfloat16_as_ushort(c2); b3 = __bfloat16_as_ushort(c3);
+        };
+        auto store_library_tmem = [&](int par) {  // A of G1: TMEM [p lane][lib pairs], three planes of 16 columns
+            uint16_t pl[3][TPT];
+#pragma unroll
+            for (int jj = 0; jj < TPT; ++jj) split_term(gv[par][jj], pl[0][jj], pl[1][jj], pl[2][jj]);
+#pragma unroll
+            for (int pa = 0; pa < 3; ++pa)
+#pragma unroll
+                for (int cc = 0; cc < TPT / 2; ++cc)
+                    tmem_st1(tmem + lane_addr + TMEM_G + pa * (KP / 2) + h + cc * NQ, (uint32_t)pl[pa][2 * cc] | ((uint32_t)pl[pa][2 * cc + 1] << 16));
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar(GT_FULL));
+        };
+        auto store_library_smem = [&](int par) {  // B of G4: G_s[lib rows][p contiguous], two planes (published with R_FULL)
             const uint32_t gs = sbase + G_OFF + (p >> 6) * (KP * 128);
             const uint32_t pb = (p & 63) * 2;
-            uint16_t pl[3][KP / NQ];
 #pragma unroll
-            for (int jj = 0; jj < KP / NQ; ++jj) {
-                const float v = gv[jj];
-                const __nv_bfloat16 b1 = __float2bfloat16_rn(v);
-                const float e1 = v - __bfloat162float(b1);
-                const __nv_bfloat16 b2 = __float2bfloat16_rn(e1);
-                const __nv_bfloat16 b3 = __float2bfloat16_rn(e1 - __bfloat162float(b2));
-                pl[0][jj] = __bfloat16_as_ushort(b1); pl[1][jj] = __bfloat16_as_ushort(b2); pl[2][jj] = __bfloat16_as_ushort(b3);
+            for (int jj = 0; jj < TPT; ++jj) {
+                uint16_t b1, b2, b3;
+                split_term(gv[par][jj], b1, b2, b3);
                 const uint32_t off = sw128(term_of(jj), pb);
-                st_shared_u16(gs + off, pl[0][jj]);
-                st_shared_u16(gs + G_PLANE + off, pl[1][jj]);
-                if (!G1_TMEM) st_shared_u16(gs + 2 * G_PLANE + off, pl[2][jj]);
+                st_shared_u16(gs + off, b1);
+                st_shared_u16(gs + G_PLANE + off, b2);
             }
-            if (G1_TMEM) {
-#pragma unroll
-                for (int pa = 0; pa < 3; ++pa)
-#pragma unroll
-                    for (int cc = 0; cc < KP / NQ / 2; ++cc)
-                        tmem_st1(tmem + lane_addr + TMEM_G + pa * (KP / 2) + h + cc * NQ, (uint32_t)pl[pa][2 * cc] | ((uint32_t)pl[pa][2 * cc + 1] << 16));
-                tmem_st_wait();
-                tc_fence_before();
-            }
-            fence_async_smem();
-            mbar_arrive(bar(G_FULL));
         };
 
+        if (my_tiles > 0) {  // first tile: nothing to overlap with
+            eval_upto(TPT);
+            store_library_tmem(0);
+        }
+        // terms per slab so that the next row is complete before the tile's last slab (which publishes it to TMEM)
+        const int ev_per = nslab > 1 ? (TPT + nslab - 2) / (nslab - 1) : TPT;
         int it = 0;
         for (int tl = 0; tl < my_tiles; ++tl) {
             const long long tile = blockIdx.x + (long long)tl * gridDim.x;
             const long long x = tile * BP + p;
             const bool xin = x < a.n;
-            long long cg0 = now();
-            if (tl == 0) eval_library(tile);
-            long long cg1 = now();
-            if (tl > 0) mbar_wait(bar(G_EMPTY), (tl - 1) & 1, 9, tl);
-            cg0 = now(); te[5] += cg0 - cg1;
-            store_library();
-            te[6] += now() - cg0;
-            if (tl > 0) store_d(tl - 1, tile - gridDim.x);
-
+            const bool have_next = tl + 1 < my_tiles;
+            ev_next = have_next ? 0 : TPT;
+            ev_tile = tl + 1;
             float lsum = 0.0f;  // fp32 over the 256 residuals of a tile, folded into the fp64 accumulator once per tile (FP64 adds are slow)
-            float ulast[U_TAIL > 0 ? U_TAIL : 1];
-            auto load_last = [&](int slab2) {  // snapshots 24..31 of this thread's quarter, straight from HBM/L2
-                if (U_TAIL == 0) return;
-                const int tb = slab2 * BT + h * QT + U_STAGES * U_ROWS;
-                const float* up = a.U + (long long)tb * a.ld + x;
-                if (xin && tb + U_TAIL <= a.m) {
-#pragma unroll
-                    for (int j = 0; j < U_TAIL; ++j, up += a.ld) ulast[j] = __ldg(up);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < U_TAIL; ++j, up += a.ld) ulast[j] = (xin && tb + j < a.m) ? __ldg(up) : 0.0f;
-                }
-            };
-            load_last(0);
             for (int slab = 0; slab < nslab; ++slab, ++it) {
                 const int t0 = slab * BT + h * QT;
                 long long c0 = now();
+                etrace(20, it);
                 mbar_wait(bar(REC_FULL), it & 1, 10, it);
                 long long c1 = now(); te[0] += c1 - c0;
+                etrace(21, it);
                 tc_fence_after();
+                if (slab == nslab - 1 && have_next) {
+                    // G1 of this tile's last slab has completed (REC_FULL): the TMEM planes of the library may take the next tile's row,
+                    // and the MMA issuer can run the next tile's first G1 ahead of this slab's G3 / G4
+                    const long long cg0 = now();
+                    eval_upto(TPT);
+                    store_library_tmem((tl + 1) & 1);
+                    te[6] += now() - cg0;
+                    etrace(30, it);
+                }
                 uint32_t u[QT];  // Rec of this thread's 32 snapshots, then r = Rec - U in place
                 if (!kSupplied) {
                     tmem_ld16(tmem + lane_addr + TMEM_REC + h * QT, u);
                     tmem_ld16(tmem + lane_addr + TMEM_REC + h * QT + 16, u + 16);
                 }
-                mbar_wait(bar(U_FULL0 + h * U_STAGES), it & 1, 11, it);
+                const int ub = (it * U_PER) % U_RING;          // ring position of this slab-tile's first stage
+                const uint32_t upar = ((it * U_PER) / U_RING) & 1;
+                mbar_wait(bar(U_FULL0 + h * U_RING + ub), upar, 11, it);
+                etrace(22, it);
                 if (!kSupplied) tmem_ld_wait();
-#ifdef EXP_EARLY_REC
-#ifdef EXP_EARLY_REC_DEP
-                {
-                    uint32_t xx = 0;
-#pragma unroll
-                    for (int j = 0; j < QT; ++j) xx ^= u[j];
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(&sink_s[lane])), "r"(xx) : "memory");
-                }
-#endif
-                tc_fence_before();
-                mbar_arrive(bar(REC_EMPTY));
-#endif
+                etrace(23, it);
                 // masked == false for every interior (tile, slab): no per-element selects in the common path
                 auto residual = [&](auto masked) {
 #pragma unroll
-                    for (int k = 0; k < U_STAGES; ++k) {
-                        const int st = h * U_STAGES + k;
-                        if (k > 0) mbar_wait(bar(U_FULL0 + st), it & 1, 11, it);
+                    for (int k = 0; k < U_PER; ++k) {
+                        const int sk = (it * U_PER + k) % U_RING;
+                        const int st = h * U_RING + sk;
+                        if (k > 0) mbar_wait(bar(U_FULL0 + st), ((it * U_PER + k) / U_RING) & 1, 11, it);
                         const uint32_t us = sbase + U_OFF + st * U_STAGE + p * 4;
 #pragma unroll
                         for (int j = 0; j < U_ROWS; ++j) {
@@ -640,9 +651,9 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                             lsum = fmaf(rr, rr, lsum);
                         }
                         {
-                            // The stage may only be released once the eight ld.shared above have RETURNED: an mbarrier arrive is not
+                            // The stage may only be released once the ld.shared above have RETURNED: an mbarrier arrive is not
                             // held back by loads still in flight, and the refilling TMA was observed to overwrite rows 5-7 of a stage
-                            // under shared-memory congestion (profiles/README.md).  A store that consumes all eight residuals
+                            // under shared-memory congestion (profiles/README.md).  A store that consumes all the residuals
                             // precedes the arrive in the same in-order pipeline.
                             uint32_t xx = 0;
 #pragma unroll
@@ -651,39 +662,30 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                         }
                         mbar_arrive(bar(U_EMPTY0 + st));
                     }
-#pragma unroll
-                    for (int j = 0; j < U_TAIL; ++j) {  // last snapshots of the quarter: prefetched into registers one slab ago
-                        float rr = kSupplied ? ulast[j] * a.seed_scale : __uint_as_float(u[U_STAGES * U_ROWS + j]) - ulast[j];
-                        if (decltype(masked)::value) rr = (xin && t0 + U_STAGES * U_ROWS + j < a.m) ? rr : 0.0f;
-                        u[U_STAGES * U_ROWS + j] = __float_as_uint(rr);
-                        lsum = fmaf(rr, rr, lsum);
-                    }
                 };
                 if (xin && (t0 + QT <= a.m)) residual(std::false_type{}); else residual(std::true_type{});
-#ifndef EXP_EARLY_REC
                 tc_fence_before();
                 mbar_arrive(bar(REC_EMPTY));
-#endif
-                // ---- r -> three bf16 planes, formed in REGISTERS while G3/G4 of the previous slab still read R_s: only the 12 vector
+                etrace(24, it);
+                // ---- r -> two bf16 planes, formed in REGISTERS while G3/G4 of the previous slab still read R_s: only the 8 vector
                 //      stores below sit between "R_s free" and "R_s full", i.e. on the tensor pipe's critical path ----
-                uint32_t w1[16], w2[16], w3[NPR == 3 ? 16 : 1];
+                uint32_t w1[16], w2[16];
 #pragma unroll
-                for (int ee = 0; ee < 16; ++ee) {
-                    if (NPR == 3) split3_pair(__uint_as_float(u[2 * ee]), __uint_as_float(u[2 * ee + 1]), w1[ee], w2[ee], w3[NPR == 3 ? ee : 0]);
-                    else split2_pair(__uint_as_float(u[2 * ee]), __uint_as_float(u[2 * ee + 1]), w1[ee], w2[ee]);
-                }
+                for (int ee = 0; ee < 16; ++ee) split2_pair(__uint_as_float(u[2 * ee]), __uint_as_float(u[2 * ee + 1]), w1[ee], w2[ee]);
                 {
                     // ptxas sinks pure arithmetic below the wait loop to shorten live ranges, which would put the whole split back on
                     // the critical path: consuming every last-plane word (each depends on the words of the planes before it) in a
                     // store that precedes the wait pins the split where it is written.  8 LOP3 + 1 STS per thread and slab.
-                    uint32_t x = 0;
+                    uint32_t xw = 0;
 #pragma unroll
-                    for (int ee = 0; ee < 16; ++ee) x ^= (NPR == 3) ? w3[NPR == 3 ? ee : 0] : w2[ee];
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(&sink_s[lane])), "r"(x) : "memory");
+                    for (int ee = 0; ee < 16; ++ee) xw ^= w2[ee];
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(&sink_s[lane])), "r"(xw) : "memory");
                 }
                 c0 = now(); te[1] += c0 - c1;
+                etrace(25, it);
                 if (it > 0) mbar_wait(bar(R_EMPTYQ0 + q), (it - 1) & 1, 12, it);
                 c1 = now(); te[2] += c1 - c0;
+                etrace(26, it);
                 // row p of box (h >> 1), 16 B chunks (h & 1) * 4 .. +3 (8 snapshots each)
                 const uint32_t rs = sbase + R_OFF + (h >> 1) * (BP * 128) + p * 128;
 #pragma unroll
@@ -694,18 +696,21 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                     const uint32_t off = ((uint32_t)(((h & 1) * 4 + c) ^ (p & 7))) << 4;
                     st_shared_v4(rs + off, w1[4 * c], w1[4 * c + 1], w1[4 * c + 2], w1[4 * c + 3]);
                     st_shared_v4(rs + R_PLANE + off, w2[4 * c], w2[4 * c + 1], w2[4 * c + 2], w2[4 * c + 3]);
-                    if (NPR == 3) {
-                        constexpr int s3 = (NPR == 3) ? 4 : 0;
-                        st_shared_v4(rs + 2 * R_PLANE + off, w3[s3 * c], w3[s3 * c + (s3 ? 1 : 0)], w3[s3 * c + (s3 ? 2 : 0)], w3[s3 * c + (s3 ? 3 : 0)]);
-                    }
                 }
+                // first slab of a tile: G4 of the previous tile has released this lane quadrant of G_s as well (same commit as R_s)
+                if (slab == 0) store_library_smem(tl & 1);
                 c0 = now(); te[4] += c0 - c1;
+                etrace(27, it);
                 fence_async_smem();
                 mbar_arrive(bar(R_FULL));
                 c1 = now(); te[7] += c1 - c0;
-                if (slab + 1 < nslab) load_last(slab + 1);  // after the fence (which would wait for them), a G3/G4 ahead of their use
-                else if (tl + 1 < my_tiles) eval_library(tile + gridDim.x);
+                etrace(28, it);
+                // slack until the next Rec: drain D of the previous tile (its G3 chain ended with that tile's last slab; the issuer
+                // holds this tile's first G3 until D_EMPTY) and evaluate the next terms of the next tile's library row
+                if (slab == 0 && tl > 0) store_d(tl - 1, tile - gridDim.x);
+                if (slab + 1 < nslab) eval_upto(min(TPT, (slab + 1) * ev_per));
                 te[3] += now() - c1;
+                etrace(29, it);
             }
             loss_acc += (double)lsum;
         }
@@ -717,18 +722,17 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         }
         if (a.dbg && lane == 0 && blockIdx.x == 0)
             for (int i = 0; i < 8; ++i) a.dbg[8192 + e * 8 + i] = te[i];
-        // last tile's chain rule, then the E accumulators of this CTA
+        // D of the last tile, then the E accumulators of this CTA
         if (my_tiles > 0) store_d(my_tiles - 1, blockIdx.x + (long long)(my_tiles - 1) * gridDim.x);
         loss_acc = warp_sum(loss_acc);
-        if (lane == 0) atomicAdd(&red_s[q * kScal + 0], loss_acc);
+        if (lane == 0) atomicAdd(&red_s[q], loss_acc);
         tc_fence_before();
     }
     __syncthreads();
-    for (int i = tid; i < kScal; i += THREADS) {
-        double s = 0.0;
-        for (int w = 0; w < 4; ++w) s += red_s[w * kScal + i];
-        a.Spart[(long long)blockIdx.x * kScal + i] = s;
-    }
+    if (kDebug && blockIdx.x == 0 && a.dbg)
+        for (int i = tid; i < 6 * TRACE_LEN; i += THREADS) a.dbg[8320 + i] = trace_s[i];
+    for (int i = tid; i < kScal; i += THREADS)
+        a.Spart[(long long)blockIdx.x * kScal + i] = (i == 0) ? (((red_s[0] + red_s[1]) + red_s[2]) + red_s[3]) : 0.0;
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
@@ -777,7 +781,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 int fused_tc_supported(const desmo_shape* s, int Kp) {
-    return (Kp <= tc::KP && s->mld <= tc::MAXSLAB * tc::BT && s->ld % 128 == 0 && s->mld % 8 == 0) ? 1 : 0;
+    return (Kp <= tc::KP && s->r <= kMaxR && s->mld <= tc::MAXSLAB * tc::BT && s->ld % 128 == 0 && s->mld % 8 == 0) ? 1 : 0;
 }
 
 void reduce_partials_launch(const float* Epart, int nx, long long ecount, const double* Spart, int nslots, int r, float* red, cudaStream_t st,
@@ -827,14 +831,14 @@ int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const flo
                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(U) failed (%d)", (int)cr); return DESMO_ERR_CUDA; }
     }
-    CUtensorMap tmup;  // L2-prefetch box: one quarter of a slab-tile
-    {
-        const cuuint64_t udims[2] = {(cuuint64_t)s->ld, (cuuint64_t)s->m};
-        const cuuint64_t ustr[1] = {(cuuint64_t)s->ld * 4};
-        const cuuint32_t ubox[2] = {(cuuint32_t)tc::BP, (cuuint32_t)tc::QT};
-        cr = enc(&tmup, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)U, udims, ustr, ubox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(U prefetch) failed (%d)", (int)cr); return DESMO_ERR_CUDA; }
+    CUtensorMap tmphi, tmp;  // rows of phi / P of one tile: box [r][128 points]
+    for (int which = 0; which < 2; ++which) {
+        const cuuint64_t ldims[2] = {(cuuint64_t)s->ld, (cuuint64_t)s->r};
+        const cuuint64_t lstr[1] = {(cuuint64_t)s->ld * 4};
+        const cuuint32_t lbox[2] = {(cuuint32_t)tc::BP, (cuuint32_t)s->r};
+        cr = enc(which ? &tmp : &tmphi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)(which ? P : phi), ldims, lstr, lbox, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(phi / P) failed (%d)", (int)cr); return DESMO_ERR_CUDA; }
     }
     TcArgs a{};
     a.U = U; a.P = P; a.phi = phi; a.omega = omega; a.dphi = dphi; a.Epart = ws.Epart; a.Spart = ws.Spart; a.Dacc = ws.Dacc;
@@ -860,13 +864,13 @@ int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const flo
     fused_event_record(0, st);
     if (supplied) {
         DESMO_CUDA(cudaFuncSetAttribute(fused_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-        fused_tc_kernel<false, true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, tm, tmu, tmup);
+        fused_tc_kernel<false, true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, tm, tmu, tmphi, tmp);
     } else if (a.dbg) {
-        DESMO_CUDA(cudaFuncSetAttribute(fused_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-        fused_tc_kernel<true, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, tm, tmu, tmup);
+        DESMO_CUDA(cudaFuncSetAttribute(fused_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES_DEBUG));
+        fused_tc_kernel<true, false><<<grid, tc::THREADS, tc::SMEM_BYTES_DEBUG, st>>>(a, tm, tmu, tmphi, tmp);
     } else {
         DESMO_CUDA(cudaFuncSetAttribute(fused_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-        fused_tc_kernel<false, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, tm, tmu, tmup);
+        fused_tc_kernel<false, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, tm, tmu, tmphi, tmp);
     }
     fused_event_record(1, st);
     DESMO_CUDA(cudaGetLastError());
