@@ -50,6 +50,12 @@ constexpr uint32_t G_PLANE = 2 * KP * 128;            // one bf16 plane of G: 2 
 // fp64 evaluation on the golden cases: 2e-7 .. 1.4e-6, the same class as a plain fp32 GEMM), far inside the 1e-5 gate, while Rec = G W
 // keeps all three planes (R is a small difference of large numbers).
 constexpr int NPR = 2;
+#ifndef DESMO_G4_COLLECT
+#define DESMO_G4_COLLECT 1
+#endif
+#ifndef DESMO_G1_WS
+#define DESMO_G1_WS 0
+#endif
 constexpr uint32_t R_OFF = 0;
 constexpr uint32_t W_OFF = R_OFF + NPR * R_PLANE;
 constexpr uint32_t G_OFF = W_OFF + 2 * W_SLAB;        // two planes (B of G4); G1 reads its three planes from TMEM
@@ -137,6 +143,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+// One try_wait without the retry loop.  A SYNCS round trip costs several hundred cycles under this kernel's shared-memory load even
+// when the phase completed long ago; a straight-line probe lets ptxas place independent work (or a second probe) under that latency,
+// which a wait loop (a branch after every attempt) cannot.  Callers fall back to mbar_wait when the probe fails.
+__device__ __forceinline__ uint32_t mbar_probe(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done;
+}
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking probe
     uint32_t done;
     asm volatile("{\n\t.reg .pred q;\n\tmbarrier.test_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
@@ -163,6 +178,46 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Collector hints: consecutive MMAs that read the SAME A tile (or, for the weight-stationary form, the same B tile) keep it in the
+// tensor core's operand collector instead of fetching it from shared memory again -- shared-memory bandwidth binds this kernel.
+// mode: 0 = plain, 1 = fill (read and keep), 2 = use (reuse and keep), 3 = lastuse (reuse and release)
+template <int kMode>
+__device__ __forceinline__ void mma_bf16_ca(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (kMode == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else if (kMode == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::use [%0], %1, %2, %3, p;\n\t}\n"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else if (kMode == 3)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        mma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+}
+// weight-stationary form, A in tensor memory, B from shared memory through collector buffer b0
+template <int kMode>
+__device__ __forceinline__ void mma_bf16_ts_wsb(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (kMode == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::fill [%0], [%1], %2, %3, p;\n\t}\n"
+                     ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else if (kMode == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::use [%0], [%1], %2, %3, p;\n\t}\n"
+                     ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else if (kMode == 3)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::lastuse [%0], [%1], %2, %3, p;\n\t}\n"
+                     ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::discard [%0], [%1], %2, %3, p;\n\t}\n"
+                     ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -314,11 +369,20 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 mbar_wait(bar(LAT_EMPTY), (lat_k - 1) & 1, 13, lat_k);
                 lat_issue();
             }
+        } else if (kDebug && lane == 1 && blockIdx.x == 0) {
+            // debug timeline: when the tensor pipe's commits actually land (polled in issue order: G1(it), then G4(it - 1))
+            for (int it = 0; it < total && it < 48; ++it) {
+                mbar_wait(bar(REC_FULL), it & 1, 15, it);
+                trace(5, 50, it);
+                if (it > 0) { mbar_wait(bar(R_EMPTYQ0 + 3), (it - 1) & 1, 16, it); trace(5, 51, it - 1); }
+            }
         }
     } else if (warp == 3 || warp == 2) {
         // ================= TMA producers: U boxes [U_ROWS snapshots][128 points]; each thread feeds the private rings of two quarters ======
         // A quarter consumes U_PER stages per slab-tile; the box of a stage is requested as soon as the stage's previous contents are
-        // consumed.  No divisions in the loop: one thread sustains ~1 TMA instruction per 400 cycles.
+        // consumed.  No divisions in the loop: one thread sustains ~1 TMA instruction per 400 cycles.  (Pulling the next slab-tile
+        // into L2 ahead of the ring -- by TMA prefetches or by plain prefetch instructions of the idle lanes -- was measured
+        // 9-18 % SLOWER, profiles/README.md: the rings are not what this kernel waits for.)
         if (elect_one_sync()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmU) : "memory");
             const int h0 = (warp - 2) * 2;
@@ -335,7 +399,6 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                         long long cp0 = now();
                         if (use > 0) mbar_wait(bar(U_EMPTY0 + b), (use - 1) & 1, 2, it);
                         tp0 += now() - cp0;
-                        if (warp == 2) trace(5, 40 + hh, it);
 #ifdef EXP_NO_UTMA
                         mbar_arrive(bar(U_FULL0 + b));
 #else
@@ -372,6 +435,20 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 // A = library planes in TMEM (16 columns per plane, 8 per k-step), B = W_s MN-major (N = snapshots, 2 boxes LBO = W_BOX)
                 const uint32_t wa_lo = ((sbase + W_OFF + buf * W_SLAB) >> 4) | ((W_BOX >> 4) << 16);
                 uint32_t acc = 0;
+#if DESMO_G1_WS
+                // weight-stationary form: the W tile of a (plane, k-step) stays in the collector for all library planes it multiplies
+#define G1_WS(PA, PB, MODE)                                                                                          \
+    mma_bf16_ts_wsb<MODE>(tmem + TMEM_REC, tmem + TMEM_G + PA * (KP / 2) + ks * 8,                                    \
+                          desc_from(wa_lo + ((PB * W_PLANE + ks * 2048) >> 4), kDescHi), idesc_g1, acc);               \
+    acc = 1;
+#ifndef EXP_NO_G1
+                if (!kSupplied) {
+#pragma unroll
+                    for (int ks = 0; ks < KP / 16; ++ks) { G1_WS(0, 2, 0) G1_WS(1, 1, 1) G1_WS(0, 1, 3) G1_WS(2, 0, 1) G1_WS(1, 0, 2) G1_WS(0, 0, 3) }
+                }
+#endif
+#undef G1_WS
+#else
 #define G1_PAIR(PA, PB)                                                                                              \
     _Pragma("unroll") for (int ks = 0; ks < KP / 16; ++ks) {                                                          \
         mma_bf16_ts(tmem + TMEM_REC, tmem + TMEM_G + PA * (KP / 2) + ks * 8,                                          \
@@ -382,6 +459,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 if (!kSupplied) { DESMO_PAIRS(G1_PAIR) }
 #endif
 #undef G1_PAIR
+#endif
                 umma_commit(bar(REC_FULL));
                 trace(0, 5, it);
             };
@@ -422,22 +500,24 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 // by lane quadrant (k-steps 2q, 2q+1 read the R_s rows and G_s columns of points 32q..32q+31 only) with one commit each:
                 // the epilogue warps of quadrant q may overwrite their part of R_s (and, at a tile boundary, of G_s) while G4 still
                 // works on the later quadrants, so only the LAST quadrant's stores are serialised between G4 of this slab and G3 of the next.
-#define G4_PAIR(PA, PB)                                                                                              \
-    _Pragma("unroll") for (int kk = 0; kk < 2; ++kk) {                                                                \
-        const int ks = 2 * qq + kk;                                                                                   \
-        mma_bf16(e_tmem, desc_from(rm_lo + ((PA * R_PLANE + ks * 2048) >> 4), kDescHi),                                \
-                 desc_from(gk_lo + ((PB * G_PLANE + (ks >> 2) * (KP * 128) + (ks & 3) * 32) >> 4), kDescHi), idesc_g4, acc); \
-        acc = 1;                                                                                                      \
-    }
+                // The two products of R's first plane read the same A tile back to back: the second takes it from the collector.
+#define G4_MMA(PA, PB, MODE)                                                                                         \
+    mma_bf16_ca<DESMO_G4_COLLECT ? MODE : 0>(e_tmem, desc_from(rm_lo + ((PA * R_PLANE + ks * 2048) >> 4), kDescHi),    \
+        desc_from(gk_lo + ((PB * G_PLANE + (ks >> 2) * (KP * 128) + (ks & 3) * 32) >> 4), kDescHi), idesc_g4, acc);    \
+    acc = 1;
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
 #ifndef EXP_NO_G4
-                    DESMO_GRAD_PAIRS(G4_PAIR)
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const int ks = 2 * qq + kk;
+                        G4_MMA(1, 0, 0) G4_MMA(0, 1, 1) G4_MMA(0, 0, 3)
+                    }
 #endif
                     umma_commit(bar(R_EMPTYQ0 + qq));
                     trace(0, 10 + qq, it);
                 }
-#undef G4_PAIR
+#undef G4_MMA
                 if (slab == nslab - 1) umma_commit(bar(D_FULL));
             };
             if (total > 0) issue_g1(0);
@@ -605,7 +685,14 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 const int t0 = slab * BT + h * QT;
                 long long c0 = now();
                 etrace(20, it);
-                mbar_wait(bar(REC_FULL), it & 1, 10, it);
+                const int ub = (it * U_PER) % U_RING;          // ring position of this slab-tile's first stage
+                const uint32_t upar = ((it * U_PER) / U_RING) & 1;
+                {
+                    // both hand-overs are normally complete by now: probe them together (one round trip instead of two)
+                    const uint32_t d_rec = mbar_probe(bar(REC_FULL), it & 1), d_u = mbar_probe(bar(U_FULL0 + h * U_RING + ub), upar);
+                    if (!d_rec) mbar_wait(bar(REC_FULL), it & 1, 10, it);
+                    if (!d_u) mbar_wait(bar(U_FULL0 + h * U_RING + ub), upar, 11, it);
+                }
                 long long c1 = now(); te[0] += c1 - c0;
                 etrace(21, it);
                 tc_fence_after();
@@ -623,9 +710,6 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                     tmem_ld16(tmem + lane_addr + TMEM_REC + h * QT, u);
                     tmem_ld16(tmem + lane_addr + TMEM_REC + h * QT + 16, u + 16);
                 }
-                const int ub = (it * U_PER) % U_RING;          // ring position of this slab-tile's first stage
-                const uint32_t upar = ((it * U_PER) / U_RING) & 1;
-                mbar_wait(bar(U_FULL0 + h * U_RING + ub), upar, 11, it);
                 etrace(22, it);
                 if (!kSupplied) tmem_ld_wait();
                 etrace(23, it);
@@ -669,9 +753,12 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 etrace(24, it);
                 // ---- r -> two bf16 planes, formed in REGISTERS while G3/G4 of the previous slab still read R_s: only the 8 vector
                 //      stores below sit between "R_s free" and "R_s full", i.e. on the tensor pipe's critical path ----
+                // (the probe of R_s' release is issued first, so that its round trip runs under the split)
+                const uint32_t d_r = it > 0 ? mbar_probe(bar(R_EMPTYQ0 + q), (it - 1) & 1) : 1u;
                 uint32_t w1[16], w2[16];
 #pragma unroll
                 for (int ee = 0; ee < 16; ++ee) split2_pair(__uint_as_float(u[2 * ee]), __uint_as_float(u[2 * ee + 1]), w1[ee], w2[ee]);
+#ifndef EXP_NO_SPLIT_PIN
                 {
                     // ptxas sinks pure arithmetic below the wait loop to shorten live ranges, which would put the whole split back on
                     // the critical path: consuming every last-plane word (each depends on the words of the planes before it) in a
@@ -681,9 +768,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                     for (int ee = 0; ee < 16; ++ee) xw ^= w2[ee];
                     asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(&sink_s[lane])), "r"(xw) : "memory");
                 }
+#endif
                 c0 = now(); te[1] += c0 - c1;
                 etrace(25, it);
-                if (it > 0) mbar_wait(bar(R_EMPTYQ0 + q), (it - 1) & 1, 12, it);
+                if (!d_r) mbar_wait(bar(R_EMPTYQ0 + q), (it - 1) & 1, 12, it);
                 c1 = now(); te[2] += c1 - c0;
                 etrace(26, it);
                 // row p of box (h >> 1), 16 B chunks (h & 1) * 4 .. +3 (8 snapshots each)

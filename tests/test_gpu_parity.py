@@ -22,11 +22,32 @@ GRAD_TOL = {"gates": 1e-5, "rows": 1e-5, "coefs": 1e-5, "periods": 5e-5, "phi": 
 PATHS = [1, 2, 3]  # DESMO_PATH_FP32 (FFMA), DESMO_PATH_TC (fused tcgen05 kernel), DESMO_PATH_GEMM (tcgen05 GEMM path, any library)
 
 
+def _covered(path, K, r, m):
+    """Shapes a path is built for: the fused tcgen05 kernel covers K <= 32, m <= 1024 (larger libraries run on the GEMM path),
+    the FFMA path K <= 80, r <= 8, the GEMM path everything.  Parametrised tests only generate covered (case, path) pairs."""
+    if path == 2:
+        return K <= 32 and m <= 1024 and r <= 8
+    if path == 1:
+        return K <= 80 and r <= 8
+    return True
+
+
 def _skip_unless_covered(path, K, r, m):
-    if path == 2 and (K > 32 or m > 1024 or r > 8):
-        pytest.skip("the fused tcgen05 kernel covers K <= 32, m <= 1024 (larger shapes run on the GEMM path)")
-    if path == 1 and (K > 80 or r > 8):
-        pytest.skip("the FFMA path covers K <= 80, r <= 8")
+    if not _covered(path, K, r, m):
+        pytest.skip("shape outside this path's coverage")
+
+
+def _n_terms(r, p, nF=None):
+    from math import comb
+    return comb(r + p, p) + 3 * r
+
+
+def _golden_pairs(names):
+    out = []
+    for name in names:
+        prm = golden_case(name)[4]
+        out += [pytest.param(name, path, id=f"{name}-path{path}") for path in PATHS if _covered(path, prm.K, prm.r, prm.m)]
+    return out
 
 
 def _engine(prm, modes, snap, path=1, **kw):
@@ -54,8 +75,7 @@ def _check_grads(e, out, beta, lam, tol_scale=1.0):
         assert err < GRAD_TOL[kk] * tol_scale, (k, err)
 
 
-@pytest.mark.parametrize("path", PATHS)
-@pytest.mark.parametrize("name", [os.path.basename(p)[:-4] for p in sorted(glob.glob(os.path.join(GOLDEN, "grad_*.npz")))])
+@pytest.mark.parametrize("name,path", _golden_pairs([os.path.basename(p)[:-4] for p in sorted(glob.glob(os.path.join(GOLDEN, "grad_*.npz")))]))
 def test_step_loss_and_grads_match_reference_golden(name, path):
     """Against the reference's own autograd outputs (fixtures made by oracle/make_golden.py)."""
     fx, meta, modes, snap, prm = golden_case(name)
@@ -96,8 +116,15 @@ CASES = [  # (kind, n, m, r, p, nF) -- ragged sizes, single tile, multi tile, ch
 ]
 
 
-@pytest.mark.parametrize("path", PATHS)
-@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}-{c[1]}x{c[2]}-r{c[3]}p{c[4]}" + (f"-nF{c[5]}" if c[5] else ""))
+def _case_id(c):
+    return f"{c[0]}-{c[1]}x{c[2]}-r{c[3]}p{c[4]}" + (f"-nF{c[5]}" if c[5] else "")
+
+
+CASE_PAIRS = [pytest.param(c, path, id=f"{_case_id(c)}-path{path}") for c in CASES for path in PATHS
+              if _covered(path, _n_terms(c[3], c[4]), c[3], c[2])]
+
+
+@pytest.mark.parametrize("case,path", CASE_PAIRS)
 def test_step_loss_and_grads_match_oracle(case, path):
     kind, n, m, r, p, nF = case
     _, modes, snap, prm = make_case(kind, n, m, r, p, nF)
@@ -110,8 +137,7 @@ def test_step_loss_and_grads_match_oracle(case, path):
     assert float(e.red[:e.Kp * e.mld].view(e.Kp, e.mld)[e.K:].abs().max()) == 0.0  # padded rows stay zero
 
 
-@pytest.mark.parametrize("path", PATHS)
-@pytest.mark.parametrize("name", ["traj_cyl_r4p3", "traj_fcyl_r2p2", "traj_default_cyl_r4p3", "traj_chan_r4p2"])
+@pytest.mark.parametrize("name,path", _golden_pairs(["traj_cyl_r4p3", "traj_fcyl_r2p2", "traj_default_cyl_r4p3", "traj_chan_r4p2"]))
 def test_training_trajectory_matches_reference_golden(name, path):
     """1000 fused steps (device Adamax + host plateau scheduler) vs the reference's torch.optim.Adamax trajectory."""
     from desmo_b200 import DesmoTrainer
@@ -214,8 +240,7 @@ def _load_final(e, fx, meta, prm, modes, snap):
     return q
 
 
-@pytest.mark.parametrize("path", PATHS)
-@pytest.mark.parametrize("name", ["traj_chan_r4p2", "traj_fcyl_r2p2", "traj_cyl_r4p3"])
+@pytest.mark.parametrize("name,path", _golden_pairs(["traj_chan_r4p2", "traj_fcyl_r2p2", "traj_cyl_r4p3"]))
 def test_threshold_sweep_matches_reference_golden(name, path):
     """Post-hoc sparsification against the REFERENCE's own sweep (CYL:1184-1265 run on the reference module by
     oracle/make_golden.py after its 1000-step run), on the same trained parameters: term norms, the exactly identical active mask
