@@ -61,6 +61,7 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.samples, self._stop = index, [], threading.Event()  # samples: (sm_mhz, sm_max_mhz, {reasons})
+        self.power_w, self.power_limit_w = [], None
         self.th = threading.Thread(target=self._run, daemon=True)
         self.source = "nvml"
 
@@ -71,9 +72,20 @@ class ClockSampler:
         h = nv.nvmlDeviceGetHandleByIndex(self.index)
         mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
         get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        try:
+            self.power_limit_w = nv.nvmlDeviceGetEnforcedPowerLimit(h) / 1000.0
+        except Exception:
+            pass
+        k = 0
         while not self._stop.is_set():
             mask = int(get_reasons(h))
             self.samples.append((int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(mx), {n for n, b in self.BITS if mask & b}))
+            if k % 8 == 0:  # board power: a slow sensor, sampled every ~16 ms
+                try:
+                    self.power_w.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
+            k += 1
             self._stop.wait(0.002)
 
     def _run_smi(self):
@@ -109,7 +121,9 @@ class ClockSampler:
         reasons = set().union(*[s[2] for s in self.samples]) if self.samples else set()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
                 "sm_max_mhz": max(s[1] for s in self.samples) if self.samples else None, "reasons": sorted(reasons),
-                "samples": len(self.samples), "source": self.source}
+                "samples": len(self.samples), "source": self.source,
+                "power_w": round(sorted(self.power_w)[len(self.power_w) // 2], 1) if self.power_w else None,
+                "power_limit_w": self.power_limit_w}
 
 
 def synth_on_device(torch, n, m, dev, seed, x_offset=0, n_global=None):

@@ -82,12 +82,18 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise DesmoError(f"{LIB_PATH} is missing and there is no CPU fallback; run `python -m desmo_b200.build`")
+    if "DESMO_B200_LIB" not in os.environ:
+        # in-tree library: (re)build when it is missing or older than the sources (build() compares a source digest and returns
+        # at once on a match), so that edited kernels are never tested against a stale binary
         from . import build as _build
 
-        _build.build()
+        try:
+            _build.build()
+        except _build.NvccMissing as e:  # no compiler here: an existing library is used as it is (a failed compile still raises)
+            if not os.path.exists(LIB_PATH):
+                raise DesmoError(f"{LIB_PATH} is missing and cannot be built ({e}); there is no CPU fallback") from e
+    elif not os.path.exists(LIB_PATH):
+        raise DesmoError(f"DESMO_B200_LIB={LIB_PATH} does not exist")
     try:
         lib = C.CDLL(LIB_PATH)
     except OSError as e:  # pragma: no cover

@@ -15,11 +15,15 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
 
+class NvccMissing(RuntimeError):
+    pass
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
             return cand
-    raise RuntimeError("nvcc not found")
+    raise NvccMissing("nvcc not found")
 
 
 def _digest() -> str:

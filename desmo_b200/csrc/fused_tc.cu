@@ -37,6 +37,14 @@ constexpr int E_FLUSH_TILES = 32;  // the tensor core adds into fp32 accumulator
 constexpr int EPI_WARPS = 16;      // 4 lane quadrants x 4 snapshot quarters
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = 128 + EPI_THREADS;
+#ifndef DESMO_SETMAXNREG
+#define DESMO_SETMAXNREG 0
+#endif
+#ifndef DESMO_REGS_EPI
+#define DESMO_REGS_EPI 112
+#define DESMO_REGS_CTRL 32
+#endif
+constexpr int REGS_EPI = DESMO_REGS_EPI, REGS_CTRL = DESMO_REGS_CTRL;  // setmaxnreg budgets (per thread) of the epilogue / control warpgroups
 constexpr int NQ = 4;              // snapshot quarters per slab
 constexpr int QT = BT / NQ;        // 32 snapshots per epilogue thread
 constexpr int TPT = KP / NQ;       // library terms evaluated per epilogue thread (the four quarters of a point share the row)
@@ -121,15 +129,15 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int t
         // the suspend-time hint lets the hardware park the thread instead of burning issue slots the epilogue math needs
         asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
                      : "=r"(done) : "r"(bar), "r"(parity), "r"(kDebug ? 2000u : 0x989680u) : "memory");
-        if (kDebug) {
-            if (!done && ++spins >= (1u << 20)) {  // debug runs only: report who is stuck, later abort the grid
-                if (spins == (1u << 20) && g_tc_dbg) {
-                    unsigned long long* d = g_tc_dbg + 4096 + (blockIdx.x * 20 + (threadIdx.x >> 5)) * 4;
-                    d[0] = 0xdead0000ull | (unsigned)tag; d[1] = (unsigned long long)iter; d[2] = parity; d[3] = threadIdx.x;
-                    __threadfence_system();
-                }
-                if (spins > (1u << 22)) __trap();
+        if (kDebug && !done && ++spins >= (1u << 20)) {
+            // debug runs report who was stuck where (production runs rely on the CTA's watchdog lane: a spin counter in every
+            // wait loop was measured to cost 6 % of the kernel)
+            if (spins == (1u << 20) && g_tc_dbg) {
+                unsigned long long* d = g_tc_dbg + 4096 + (blockIdx.x * 20 + (threadIdx.x >> 5)) * 4;
+                d[0] = 0xdead0000ull | (unsigned)tag; d[1] = (unsigned long long)iter; d[2] = parity; d[3] = threadIdx.x;
+                __threadfence_system();
             }
+            if (spins > (1u << 22)) __trap();
         }
     }
 }
@@ -286,6 +294,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
     __shared__ float omega_s[3 * kMaxR];
     __shared__ uint32_t desc_s[KP];  // packed description of library term j: kind | deg << 3 | mode indices (3 bits each) << 6
     __shared__ double red_s[4];
+    __shared__ volatile int progress_s;  // slab-tiles the MMA issuer has completed issuing (watchdog)
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -321,6 +330,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid < 4) red_s[tid] = 0.0;
+    if (tid == 0) progress_s = 0;
     if (tid < 3 * a.r) omega_s[tid] = a.omega[tid];
     if (tid >= 64 && tid < 64 + KP) {
         // term j of the library (CYL:376-434 column order, then the sin / cos / tanh blocks of CYL:565-567)
@@ -341,6 +351,13 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
 
+    // Register budget (setmaxnreg, per warpgroup of four warps): the control warpgroup keeps 32 registers per thread and hands the rest
+    // of its launch-time allocation to the four epilogue warpgroups -- 128 * 32 + 512 * 112 = 640 * 96.  With 112 registers the
+    // epilogue keeps its addresses and loop invariants resident instead of rematerialising them every slab (and nothing spills).
+    if (warp < 4) {
+#if DESMO_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
+#endif
     if (warp == 0) {
         // ======================== TMA producer: W slab planes; phi / P rows of the tile whose library is evaluated next ========================
         if (elect_one_sync()) {
@@ -368,6 +385,18 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             while (lat_k < my_tiles) {
                 mbar_wait(bar(LAT_EMPTY), (lat_k - 1) & 1, 13, lat_k);
                 lat_issue();
+            }
+        } else if (lane == 2) {
+            // Watchdog: a protocol error must fail the launch, not hang the GPU.  One otherwise idle lane naps and checks that the
+            // MMA issuer keeps advancing; ~1 s without progress traps.
+            int last = -1;
+            unsigned idle = 0;
+            for (;;) {
+                const int pr = progress_s;
+                if (pr >= total) break;
+                if (pr != last) { last = pr; idle = 0; }
+                else if (++idle > 50000u) __trap();
+                __nanosleep(20000);
             }
         } else if (kDebug && lane == 1 && blockIdx.x == 0) {
             // debug timeline: when the tensor pipe's commits actually land (polled in issue order: G1(it), then G4(it - 1))
@@ -525,10 +554,15 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
                 // run ahead, across tile boundaries too: the tensor pipe works on G1 of the next slab-tile while the epilogue forms R
                 if (it + 1 < total) issue_g1(it + 1);
                 issue_g34(it);
+                progress_s = it + 1;
             }
             if (a.dbg) for (int i = 0; i < 5; ++i) a.dbg[blockIdx.x * 32 + i] = tm[i];
         }
-    } else if (warp >= 4) {
+    }
+    } else {
+#if DESMO_SETMAXNREG
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+#endif
         // ================================================ epilogue warps ================================================
         // thread <-> (mesh point p == TMEM lane, quarter h of the slab's snapshots): 16 warps, q = lane quadrant, h = snapshots 32h..32h+31
         const int e = warp - 4, q = e & 3, h = e >> 2;
