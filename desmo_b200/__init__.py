@@ -6,7 +6,8 @@ nvcc) and fails loudly when it, or a CUDA device, is missing -- there is no CPU 
 from ._lib import DesmoError, PATH_AUTO, PATH_FP32, PATH_GEMM, PATH_TC  # noqa: F401
 from .engine import REFERENCE_LRS, DesmoEngine  # noqa: F401
 from .model import DESMO, DESMOFourier  # noqa: F401
+from .autoencoder import Autoencoder_Linear_Temporal, SINDyAutoencoder  # noqa: F401
 from .trainer import DesmoTrainer, PlateauScheduler  # noqa: F401
 
-__all__ = ["DESMO", "DESMOFourier", "DesmoEngine", "DesmoTrainer", "PlateauScheduler", "DesmoError", "REFERENCE_LRS",
+__all__ = ["DESMO", "DESMOFourier", "SINDyAutoencoder", "Autoencoder_Linear_Temporal", "DesmoEngine", "DesmoTrainer", "PlateauScheduler", "DesmoError", "REFERENCE_LRS",
            "PATH_AUTO", "PATH_FP32", "PATH_TC", "PATH_GEMM"]

@@ -277,16 +277,30 @@ __global__ void __launch_bounds__(kTile) chain_rule_kernel(const FusedArgs a, in
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long x = tile * kTile + tid;
         const bool xin = x < a.n;
-        for (int i = 0; i < r; ++i) {
-            Phi_s[i * kTile + tid] = (x < a.ld) ? a.phi[(long long)i * a.ld + x] * a.P[(long long)i * a.ld + x] : 0.0f;
-            dPhi_s[i * kTile + tid] = 0.0f;
+        // all global loads of the tile first, in batches of independent requests (the kernel is latency-bound otherwise: every
+        // thread reads K + 2r scattered floats): D rows of the monomials -> A_s, the trig rows and the POD modes -> registers
+        float pod[R], dtrig[3 * R];
+#pragma unroll
+        for (int i = 0; i < r; ++i) pod[i] = (x < a.ld) ? __ldg(a.P + (long long)i * a.ld + x) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < r; ++i) Phi_s[i * kTile + tid] = (x < a.ld) ? __ldg(a.phi + (long long)i * a.ld + x) * pod[i] : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 3 * r; ++i) dtrig[i] = xin ? __ldg(a.Dacc + (long long)(T + i) * a.ld + x) * a.scale : 0.0f;
+        for (int j0 = 0; j0 < T; j0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (xin && j0 + u < T) ? __ldg(a.Dacc + (long long)(j0 + u) * a.ld + x) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (j0 + u < T) A_s[(j0 + u) * kTile + tid] = v[u] * a.scale;
         }
+#pragma unroll
+        for (int i = 0; i < r; ++i) dPhi_s[i * kTile + tid] = 0.0f;
         L_s[tid] = 1.0f;
         for (int j = 1; j < T; ++j) {
             const float f = Phi_s[a.mt.last[j] * kTile + tid];
             L_s[j * kTile + tid] = (a.mt.deg[j] == 1) ? f : L_s[a.mt.parent[j] * kTile + tid] * f;
         }
-        for (int j = 0; j < T; ++j) A_s[j * kTile + tid] = xin ? a.Dacc[(long long)j * a.ld + x] * a.scale : 0.0f;
         for (int j = T - 1; j >= 1; --j) {
             const float adj = A_s[j * kTile + tid];
             const int par = a.mt.parent[j], v = a.mt.last[j];
@@ -295,18 +309,13 @@ __global__ void __launch_bounds__(kTile) chain_rule_kernel(const FusedArgs a, in
         }
 #pragma unroll
         for (int i = 0; i < r; ++i) {
-            const float ph = Phi_s[i * kTile + tid], pod = (x < a.ld) ? a.P[(long long)i * a.ld + x] : 0.0f;
+            const float ph = Phi_s[i * kTile + tid];
             const float ws = a.omega[3 * i], wc = a.omega[3 * i + 1], wh = a.omega[3 * i + 2];
-            float ds = 0.0f, dc = 0.0f, dh = 0.0f;
-            if (xin) {
-                ds = a.Dacc[(long long)(T + i) * a.ld + x] * a.scale;
-                dc = a.Dacc[(long long)(T + r + i) * a.ld + x] * a.scale;
-                dh = a.Dacc[(long long)(T + 2 * r + i) * a.ld + x] * a.scale;
-            }
+            const float ds = dtrig[i], dc = dtrig[r + i], dh = dtrig[2 * r + i];
             const float cs = cosf(ws * ph), sn = sinf(wc * ph), th = tanhf(wh * ph);
             const float sech2 = 1.0f - th * th;
             const float dphi_i = dPhi_s[i * kTile + tid] + (ds * ws * cs - dc * wc * sn + dh * wh * sech2);
-            if (x < a.ld) a.dphi[(long long)i * a.ld + x] = dphi_i * pod;
+            if (x < a.ld) a.dphi[(long long)i * a.ld + x] = dphi_i * pod[i];
             om_acc[3 * i] += ds * ph * cs;
             om_acc[3 * i + 1] -= dc * ph * sn;
             om_acc[3 * i + 2] += dh * ph * sech2;
@@ -371,20 +380,36 @@ static cudaError_t chain_rule_dispatch(const FusedArgs& a, int slot_base, int gc
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ Epart, int nx, long long ecount,
                                                               const double* __restrict__ Spart, int nslots, int r, float* __restrict__ red,
                                                               int what) {
-    __shared__ float part_s[8][32];
+    // E: a CTA owns 128 consecutive outputs (one float4 per lane); warp w adds the partials b = w, w + 8, ... four at a time (four
+    // independent 512 B loads in flight per warp), then the eight warp sums are added in warp order.  The partials were just written
+    // by the fused kernel and sit in L2: the kernel is latency-bound, hence the wide, batched loads.  ecount is a multiple of 4.
+    __shared__ float4 part_s[8][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const long long o = (long long)blockIdx.x * 32 + lane;
+    const long long o = ((long long)blockIdx.x * 32 + lane) * 4;
     if (what & 1) {
-        float s = 0.0f;
-        if (o < ecount)
-            for (int b = w; b < nx; b += 8) s += __ldg(Epart + (long long)b * ecount + o);
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o < ecount) {
+            const float4* src = reinterpret_cast<const float4*>(Epart + o);
+            const long long stride = ecount / 4;
+            int b = w;
+            for (; b + 24 < nx; b += 32) {
+                const float4 v0 = __ldcg(src + (long long)b * stride), v1 = __ldcg(src + (long long)(b + 8) * stride);
+                const float4 v2 = __ldcg(src + (long long)(b + 16) * stride), v3 = __ldcg(src + (long long)(b + 24) * stride);
+                s.x = (((s.x + v0.x) + v1.x) + v2.x) + v3.x; s.y = (((s.y + v0.y) + v1.y) + v2.y) + v3.y;
+                s.z = (((s.z + v0.z) + v1.z) + v2.z) + v3.z; s.w = (((s.w + v0.w) + v1.w) + v2.w) + v3.w;
+            }
+            for (; b < nx; b += 8) {
+                const float4 v = __ldcg(src + (long long)b * stride);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+        }
         part_s[w][lane] = s;
         __syncthreads();
         if (w == 0 && o < ecount) {
-            float t = part_s[0][lane];
+            float4 t = part_s[0][lane];
 #pragma unroll
-            for (int k = 1; k < 8; ++k) t += part_s[k][lane];
-            red[o] = t;
+            for (int k = 1; k < 8; ++k) { const float4 v = part_s[k][lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+            *reinterpret_cast<float4*>(red + o) = t;
         }
     }
     if ((what & 2) && blockIdx.x == 0 && threadIdx.x < kScal) {
@@ -401,15 +426,15 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
                 red[ecount + 1 + gj * r + gi] = (float)s;
             }
         } else {
-            const int w = i - 1 - kMaxR * kMaxR;
-            if (w < 3 * r) red[ecount + 1 + r * r + w] = (float)s;
+            const int w2 = i - 1 - kMaxR * kMaxR;
+            if (w2 < 3 * r) red[ecount + 1 + r * r + w2] = (float)s;
         }
     }
 }
 
 void reduce_partials_launch(const float* Epart, int nx, long long ecount, const double* Spart, int nslots, int r, float* red, cudaStream_t st,
                             int what) {
-    const unsigned grid = (what & 1) ? (unsigned)((ecount + 31) / 32) : 1u;
+    const unsigned grid = (what & 1) ? (unsigned)((ecount + 127) / 128) : 1u;
     reduce_partials_kernel<<<grid, 256, 0, st>>>(Epart, nx, ecount, Spart, nslots, r, red, what);
 }
 
@@ -500,7 +525,7 @@ int fused_fp32(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const f
     }
     if (rc) return rc;
     const long long ecount = (long long)Kp * s->mld;
-    reduce_partials_kernel<<<(unsigned)((ecount + 31) / 32), 256, 0, st>>>(ws.Epart, gx, ecount, ws.Spart, nslots, s->r, red, 3);
+    reduce_partials_launch(ws.Epart, gx, ecount, ws.Spart, nslots, s->r, red, st, 3);
     DESMO_CUDA(cudaGetLastError());
     return DESMO_OK;
 }
