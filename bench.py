@@ -273,6 +273,10 @@ def main():
     ap.add_argument("--modes", type=int, default=0, help="override r")
     ap.add_argument("--polyorder", type=int, default=-1, help="override polyorder")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 fp32 FFMA, 2 fused tcgen05, 3 tcgen05 GEMM path")
+    ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: inter-rank sum of the partials -- one-shot exchange over NVLink peer memory (csrc/peer.cu) or NCCL")
+    ap.add_argument("--host-scheduler", action="store_true",
+                    help="step ReduceLROnPlateau on the host like the reference (one D2H sync per scheduler epoch) instead of inside the captured step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pod", action="store_true", help="profiling runs: random orthonormal-scale modes instead of the POD init")
@@ -300,6 +304,8 @@ def main():
         return {"workload": f"{args.workload}: {n_local} points/GPU x {m} snapshots, r={r}, polyorder={p}" + (f", nF={nF}" if nF else "") +
                 f", fp32, point-sharded, {args.scaling} scaling", "points_per_gpu": n_local, "points_total": n_global, "snapshots": m, "r": r,
                 "polyorder": p, "scheduler_every": sched_every,
+                "scheduler": ("ReduceLROnPlateau on the host (one D2H sync per scheduler epoch)" if getattr(args, "host_scheduler", False) else
+                              "ReduceLROnPlateau inside the captured step (desmo_plateau_step): same schedule, no host round trip"),
                 "cache": "inputs larger than L2 (streamed from HBM every step)" if n_local * m * 4 > 4e8 else "L2 flushed between steps"}
 
     if args.impl == "reference":
@@ -364,8 +370,11 @@ def main():
         # executed on the tensor pipe as 6 bf16 passes over 128-padded tiles of the upper triangle
         pod_info["gram_tensor_tflops_bf16_executed"] = 6 * 2.0 * n * (nt * (nt + 1) // 2) * 128 * 128 / (pod_info["gram_ms"] * 1e-3) / 1e12
     torch.cuda.synchronize()
+    if world > 1 and args.allreduce == "peer":
+        e.enable_peer_allreduce()  # collective; falls back to NCCL (peer_status says why) when peer-mapped memory is unavailable
     launches_per_step, launches_src = count_graph_kernels(torch, e)
-    trainer = DesmoTrainer(model, beta=beta, patience=patience, sched_every=sched_every, use_cuda_graph=True)
+    trainer = DesmoTrainer(model, beta=beta, patience=patience, sched_every=sched_every, use_cuda_graph=True,
+                           device_scheduler=not args.host_scheduler)
 
     def barrier():
         if world > 1:
@@ -495,10 +504,13 @@ def main():
                 "global_iters_per_s": 1.0 / (ms_step * 1e-3),
                 "snapshot_gbs": 4.0 * n_global * m / (ms_step * 1e-3) / 1e9,
                 "roofline": roof, "clocks": clk.summary(), "e2e": e2e,
-                "gpu_launches": launches_per_step * args.steps + (args.steps if world > 1 else 0),
+                "gpu_launches": launches_per_step * args.steps + (args.steps if world > 1 and e._peer is None else 0),
                 "gpu_launches_per_step": launches_per_step, "gpu_launches_source": launches_src,
                 "losses_last_step": losses, "pod_sigma": [float(v) for v in sigma.tolist()], "pod_init": pod_info,
-                "path": _lib.PATH_NAMES[e.path_used]}
+                "path": _lib.PATH_NAMES[e.path_used],
+                "allreduce": ("none (single GPU)" if world == 1 else
+                              "peer memory, one-shot, rank-ordered (csrc/peer.cu)" if e._peer is not None else
+                              f"NCCL (peer exchange {e.peer_status})")}
         if parity is not None:
             line["sharded_parity"] = parity
         try:

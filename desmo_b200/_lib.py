@@ -54,6 +54,9 @@ SIGNATURES: Dict[str, tuple] = {
     "desmo_pod_eig": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "desmo_pod_project": (C.c_int, [_SP] + [_vp] * 5),
     "desmo_preprocess": (C.c_int, [_SP, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "desmo_plateau_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "desmo_peer_begin_step": (C.c_int, [_vp, _vp]),
+    "desmo_peer_allreduce": (C.c_int, [_vp, _i64, _vp, _vp]),
     "desmo_session_create": (C.c_int, [_i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
     "desmo_session_create_sharded": (C.c_int, [_i64, _i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
     "desmo_session_set_allreduce": (C.c_int, [_vp, _vp, _vp]),

@@ -169,6 +169,11 @@ int32_t desmo_padded_k(int32_t r, int32_t polyorder) {
     return T < 0 ? -1 : (T + 3 * r + 15) / 16 * 16;
 }
 
+int desmo_plateau_step(desmo_plateau* state_dev, const int32_t* step_dev, const float* losses_dev, float* hyper_dev, void* stream) {
+    if (!state_dev || !step_dev || !losses_dev || !hyper_dev) { set_error("desmo_plateau_step: null pointer"); return DESMO_ERR_ARG; }
+    return launch_plateau(state_dev, step_dev, losses_dev, hyper_dev, (cudaStream_t)stream);
+}
+
 int64_t desmo_red_count(const desmo_shape* s) {
     Dims d;
     if (validate_shape(s, &d)) return -1;

@@ -87,6 +87,7 @@ int tc_debug_read(uint64_t* out, int count);
 int fused_event_ms(float* ms);
 void fused_event_record(int which, cudaStream_t st);
 int launch_update(const UpdateArgs& a, cudaStream_t st);
+int launch_plateau(desmo_plateau* st, const int32_t* step_dev, const float* losses, float* hyper, cudaStream_t stream);
 int launch_reconstruct(const EvalArgs& a, cudaStream_t st);
 int launch_colnorm2(const EvalArgs& a, cudaStream_t st);
 int launch_term_norms(const float* g2, const float* gates, const float* rows, int T, int K, int m, int mld, int fourier_quirk, double* out,

@@ -253,4 +253,36 @@ int launch_update(const UpdateArgs& a, cudaStream_t st) {
     return DESMO_OK;
 }
 
+// ReduceLROnPlateau.step(total_loss) on the device (torch semantics: mode 'min', threshold_mode 'rel', cooldown 0).
+__global__ void plateau_kernel(desmo_plateau* st, const int32_t* step_dev, const float* losses, float* hyper) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int epoch = *step_dev - 1;  // the epoch whose update just ran (build_w advanced the counter at its start)
+    if (epoch < 0 || epoch % st->every != 0) return;
+    const double metric = (double)losses[3];
+    if (metric < st->best * (1.0 - st->threshold)) {
+        st->best = metric;
+        st->num_bad = 0;
+    } else {
+        st->num_bad += 1;
+    }
+    if (st->num_bad > st->patience) {
+        for (int i = 0; i < st->n_groups; ++i) {
+            const double old = st->lrs[i];
+            const double nw = fmax(old * st->factor, st->min_lr);
+            if (old - nw > st->eps) {
+                st->lrs[i] = nw;
+                hyper[i] = (float)nw;
+            }
+        }
+        st->num_bad = 0;
+        st->reductions += 1;
+    }
+}
+
+int launch_plateau(desmo_plateau* st, const int32_t* step_dev, const float* losses, float* hyper, cudaStream_t stream) {
+    plateau_kernel<<<1, 32, 0, stream>>>(st, step_dev, losses, hyper);
+    DESMO_CUDA(cudaGetLastError());
+    return DESMO_OK;
+}
+
 }  // namespace desmo

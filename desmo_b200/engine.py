@@ -22,6 +22,10 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+class _PeerDesc(C.Structure):  # desmo_peer (include/desmo_b200.h)
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("red_ptrs", C.c_void_p), ("flag_ptrs", C.c_void_p), ("state", C.c_void_p)]
+
+
 class DesmoEngine:
     def __init__(self, n: int, m: int, polyorder: int, r: int, omega_init: float = 10000.0, nF: Optional[int] = None,
                  period_init: float = 60.0, device: Optional[torch.device] = None, n_global: Optional[int] = None,
@@ -63,7 +67,13 @@ class DesmoEngine:
             self.rows[:, :self.m] = 1.0
         self.omega, self.omega_m, self.omega_u = torch.full((3 * self.r,), float(omega_init), **f32), z(3 * self.r), z(3 * self.r)
         self.W = z(self.Kp, self.mld)
-        self.red = z(int(self.lib.desmo_red_count(C.byref(self.shape))))
+        cnt = int(self.lib.desmo_red_count(C.byref(self.shape)))
+        self._red_pad = z((cnt + 3) // 4 * 4)   # the peer exchange moves float4s
+        self.red = self._red_pad[:cnt]
+        self.red_local: Optional[torch.Tensor] = None   # peer mode: this rank's contribution, in peer-mapped memory
+        self._peer: Optional[_PeerDesc] = None
+        self.peer_status = "off"
+        self.plateau_state: Optional[torch.Tensor] = None   # desmo_plateau on the device (DesmoTrainer(device_scheduler=True))
         self.hyper = z(_lib.HYP_COUNT)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.losses = z(4)
@@ -97,6 +107,12 @@ class DesmoEngine:
         self.hyper_host = [float(v) for v in vals]
         self.hyper.copy_(torch.tensor(self.hyper_host, dtype=torch.float32), non_blocking=False)
 
+    def _refresh_hyper_host(self) -> None:
+        """A device-side scheduler (desmo_plateau_step) lowers the learning rates in ``hyper`` without the host knowing: re-read them
+        before code that saves / restores the hyper-parameters through the host mirror."""
+        if self.plateau_state is not None:
+            self.hyper_host = [float(v) for v in self.hyper.tolist()]
+
     def reset_optimizer(self) -> None:
         for t in (self.phi_m, self.phi_u, self.gates_m, self.gates_u, self.rows_m, self.rows_u, self.omega_m, self.omega_u,
                   self.coefs_m, self.coefs_u, self.periods_m, self.periods_u):
@@ -117,12 +133,59 @@ class DesmoEngine:
                                      _ptr(self.W), _ptr(self.step_dev) if advance_step else None, _ptr(self.workspace),
                                      self._stream()), "desmo_build_w")
 
-    def fused_residual_grad(self) -> None:
+    def fused_residual_grad(self, red: Optional[torch.Tensor] = None) -> None:
         if self.U is None:
             raise _lib.DesmoError("no snapshot matrix set (call set_snapshot)")
         check(self.lib.desmo_fused_residual_grad(C.byref(self.shape), _ptr(self.U), _ptr(self.P), _ptr(self.phi), _ptr(self.omega),
-                                                 _ptr(self.W), _ptr(self.dphi), _ptr(self.red), _ptr(self.workspace), self._stream()),
+                                                 _ptr(self.W), _ptr(self.dphi), _ptr(self.red if red is None else red),
+                                                 _ptr(self.workspace), self._stream()),
               "desmo_fused_residual_grad")
+
+    def enable_peer_allreduce(self, group=None) -> bool:
+        """Point-sharded runs on one node: replaces the two NCCL all-reduces of the train step by the one-shot exchange over NVLink /
+        NVSwitch peer memory (csrc/peer.cu: every rank reads all ranks' `red` directly and adds them in rank order).  Collective: every
+        rank of the group must call it.  Returns False -- and the step keeps using NCCL -- when peer-mapped (symmetric) memory is not
+        available; ``peer_status`` says why."""
+        import torch.distributed as dist
+
+        if not self._sharded():
+            self.peer_status = "off (not sharded)"
+            return False
+        pg = group or self.pg or dist.group.WORLD
+        world, rank = dist.get_world_size(pg), dist.get_rank(pg)
+        ok = torch.ones(1, device=self.device)
+        sym = hdl = None
+        why = ""
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            if world > 16:
+                raise RuntimeError("more than DESMO_MAX_PEERS ranks")
+            cnt4 = self._red_pad.numel()
+            sym = symm.empty(cnt4 + 64, dtype=torch.float32, device=self.device)  # [red | 2 * world uint32 flags]
+            sym.zero_()
+            hdl = symm.rendezvous(sym, pg.group_name)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) != world or any(p == 0 for p in ptrs):
+                raise RuntimeError("rendezvous returned no peer pointers")
+        except Exception as ex:  # noqa: BLE001  (any failure of the optional transport keeps the NCCL path)
+            ok.zero_()
+            why = f"{type(ex).__name__}: {ex}"
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=pg)  # all ranks or none
+        if float(ok.item()) < 1.0:
+            self.peer_status = "off (symmetric memory unavailable" + (": " + why if why else " on a peer") + ")"
+            return False
+        cnt4 = self._red_pad.numel()
+        self._peer_keep = (sym, hdl,
+                           torch.tensor(ptrs + [p + 4 * cnt4 for p in ptrs], dtype=torch.int64, device=self.device),
+                           torch.zeros(2, dtype=torch.int32, device=self.device))
+        tbl, state = self._peer_keep[2], self._peer_keep[3]
+        self.red_local = sym[:self.red.numel()]
+        self._peer = _PeerDesc(world, rank, tbl.data_ptr(), tbl.data_ptr() + 8 * world, state.data_ptr())
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=pg)  # every pad is zeroed before anybody signals
+        self.peer_status = f"on ({world} ranks, one-shot exchange over peer memory)"
+        return True
 
     def all_reduce(self) -> None:
         if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
@@ -149,6 +212,12 @@ class DesmoEngine:
             self.build_w(True)
             if not self._sharded():
                 self.fused_residual_grad()
+            elif self._peer is not None:
+                # one-shot exchange over NVLink peer memory: no NCCL call, no side stream
+                st = self._stream()
+                check(self.lib.desmo_peer_begin_step(C.byref(self._peer), st), "desmo_peer_begin_step")
+                self.fused_residual_grad(self.red_local)
+                check(self.lib.desmo_peer_allreduce(C.byref(self._peer), self._red_pad.numel(), _ptr(self._red_pad), st), "desmo_peer_allreduce")
             else:
                 if self.U is None:
                     raise _lib.DesmoError("no snapshot matrix set (call set_snapshot)")
@@ -166,9 +235,13 @@ class DesmoEngine:
                 torch.distributed.all_reduce(self.red[ecount:], group=self.pg)
                 main.wait_stream(self._side)
             self.adamax_update()
+            if self.plateau_state is not None:  # ReduceLROnPlateau.step(total_loss) of this epoch, on the device
+                check(self.lib.desmo_plateau_step(_ptr(self.plateau_state), _ptr(self.step_dev), _ptr(self.losses), _ptr(self.hyper),
+                                                  self._stream()), "desmo_plateau_step")
 
     def gradients(self, beta: Optional[float] = None, l1_lambda: Optional[float] = None) -> dict:
         """d total_loss / d every packed parameter (what total_loss.backward() leaves in .grad, CYL:766)."""
+        self._refresh_hyper_host()
         saved = list(self.hyper_host)
         if beta is not None or l1_lambda is not None:
             self.set_hyper(saved[:5], saved[5] if beta is None else beta, saved[6] if l1_lambda is None else l1_lambda)
@@ -203,6 +276,7 @@ class DesmoEngine:
         f32 = dict(dtype=torch.float32, device=self.device)
         gr = torch.zeros(self.m, self.ld, **f32)  # the layout of U: pitch ld, pad columns zero
         gr[:, :self.n].copy_(grad_recon)
+        self._refresh_hyper_host()
         saved = list(self.hyper_host)
         self.set_hyper(saved[:5], 0.0, 0.0)  # no regulariser terms: pure chain rule of the upstream gradient
         g = {"gates": torch.zeros(self.K, **f32), "omega": torch.zeros(3 * self.r, **f32), "phi": torch.zeros(self.r, self.ld, **f32)}

@@ -7,6 +7,7 @@ on the epochs where the reference prints / steps the scheduler, not with an ``.i
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from typing import List, Optional, Sequence
 
@@ -40,9 +41,20 @@ class PlateauScheduler:
         return changed
 
 
+class _PlateauState(ctypes.Structure):  # desmo_plateau (include/desmo_b200.h)
+    _fields_ = [("best", ctypes.c_double), ("lrs", ctypes.c_double * 5), ("threshold", ctypes.c_double), ("factor", ctypes.c_double),
+                ("min_lr", ctypes.c_double), ("eps", ctypes.c_double), ("num_bad", ctypes.c_int32), ("patience", ctypes.c_int32),
+                ("every", ctypes.c_int32), ("n_groups", ctypes.c_int32), ("reductions", ctypes.c_int32), ("pad", ctypes.c_int32)]
+
+
 class DesmoTrainer:
+    """The loop of CYL:699-786.  ``device_scheduler=True`` runs ReduceLROnPlateau inside the captured step (desmo_plateau_step) instead
+    of on the host: identical learning-rate trajectory, but no device->host round trip per scheduler epoch -- ``step()`` then returns
+    the losses only every ``log_every`` epochs (0: never; read ``engine.losses`` or call ``sync_scheduler()`` when needed)."""
+
     def __init__(self, model, lrs: Sequence[float] = REFERENCE_LRS, beta: float = 1e-3, l1_lambda: float = 1e-4,
-                 patience: int = 1000, sched_every: int = 10, use_cuda_graph: bool = True):
+                 patience: int = 1000, sched_every: int = 10, use_cuda_graph: bool = True, device_scheduler: bool = False,
+                 log_every: int = 0):
         self.model = model
         self.engine: DesmoEngine = model.engine if hasattr(model, "engine") else model
         n_groups = 5 if self.engine.nF else 4
@@ -54,6 +66,34 @@ class DesmoTrainer:
         self.engine.set_hyper(self.scheduler.lrs, self.beta, self.l1_lambda)
         self.use_cuda_graph = use_cuda_graph
         self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self.device_scheduler, self.log_every = bool(device_scheduler), int(log_every)
+        self._plateau_dev: Optional[torch.Tensor] = None
+        if self.device_scheduler:
+            self._push_scheduler()
+
+    # ---- device-side scheduler state <-> the host mirror (self.scheduler) ----
+    def _push_scheduler(self) -> None:
+        sc = self.scheduler
+        st = _PlateauState()
+        st.best, st.threshold, st.factor, st.min_lr, st.eps = sc.best, sc.threshold, sc.factor, sc.min_lr, sc.eps
+        for i in range(5):
+            st.lrs[i] = sc.lrs[i] if i < len(sc.lrs) else 0.0
+        st.num_bad, st.patience, st.every, st.n_groups, st.reductions = sc.num_bad, sc.patience, self.sched_every, len(sc.lrs), 0
+        raw = torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8)
+        if self._plateau_dev is None:
+            self._plateau_dev = torch.zeros(ctypes.sizeof(_PlateauState), dtype=torch.uint8, device=self.engine.device)
+        self._plateau_dev.copy_(raw)
+        self.engine.plateau_state = self._plateau_dev
+
+    def sync_scheduler(self) -> PlateauScheduler:
+        """Device scheduler: reads its state back into ``self.scheduler`` (one D2H copy).  No-op for the host scheduler."""
+        if self.device_scheduler and self._plateau_dev is not None:
+            st = _PlateauState.from_buffer_copy(bytes(self._plateau_dev.cpu().numpy().tobytes()))
+            sc = self.scheduler
+            sc.best, sc.num_bad = st.best, st.num_bad
+            sc.lrs = [st.lrs[i] for i in range(len(sc.lrs))]
+            self.engine.hyper_host[:len(sc.lrs)] = [float(v) for v in sc.lrs]
+        return self.scheduler
 
     def _launch(self) -> None:
         if not self.use_cuda_graph:
@@ -93,6 +133,12 @@ class DesmoTrainer:
             self.model.sync_parameters()
         self._launch()
         out = None
+        if self.device_scheduler:
+            if self.log_every and self.epoch % self.log_every == 0:
+                out = tuple(float(v) for v in self.engine.losses.tolist())
+                self.history.append((self.epoch, *out))
+            self.epoch += 1
+            return out
         if self.epoch % self.sched_every == 0:
             vals = tuple(float(v) for v in self.engine.losses.tolist())  # the only D2H sync
             self.history.append((self.epoch, *vals))
@@ -109,6 +155,7 @@ class DesmoTrainer:
         e = self.engine
         opt = {k: getattr(e, k).detach().clone() for k in ("phi_m", "phi_u", "gates_m", "gates_u", "rows_m", "rows_u", "omega_m", "omega_u",
                                                            "coefs_m", "coefs_u", "periods_m", "periods_u") if getattr(e, k) is not None}
+        self.sync_scheduler()
         return {"model": {k: v.detach().clone() for k, v in self.model.state_dict().items()} if hasattr(self.model, "state_dict") else None,
                 "optimizer": opt, "step": int(e.step_dev.item()), "pod_modes": e.P[:, :e.n].detach().clone(),
                 "scheduler": {"lrs": list(self.scheduler.lrs), "best": self.scheduler.best, "num_bad": self.scheduler.num_bad,
@@ -141,6 +188,8 @@ class DesmoTrainer:
         self.sched_every = int(sd.get("sched_every", self.sched_every))
         self.epoch, self.beta, self.l1_lambda = int(sd["epoch"]), float(sd["beta"]), float(sd["l1_lambda"])
         e.set_hyper(self.scheduler.lrs, self.beta, self.l1_lambda)
+        if self.device_scheduler:
+            self._push_scheduler()
 
     def fit(self, snapshot: torch.Tensor, epochs: int, log_every: int = 0):
         self.engine.set_snapshot(snapshot)

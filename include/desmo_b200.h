@@ -179,6 +179,45 @@ int desmo_pod_project(const desmo_shape* s, const float* U, const float* V, cons
 int desmo_preprocess(const desmo_shape* s, const void* V, int32_t v_dtype, int64_t v_ld, int32_t m_in, int32_t t_stride,
                      int32_t d_in, int32_t d_use, int32_t flags, float* U, double* mean, void* stream);
 
+/* torch.optim.lr_scheduler.ReduceLROnPlateau (mode 'min', relative threshold, cooldown 0; CYL:614,776-778, ANEU:613) ON THE DEVICE:
+ * the reference steps it on the host with `total_loss`, i.e. one device->host round trip per scheduler epoch.  desmo_plateau_step is
+ * enqueued after desmo_adamax_update of an epoch: on epochs where (epoch % every == 0) it applies the scheduler to losses[3] and
+ * writes the (possibly reduced) learning rates into hyper[0 .. n_groups) for the NEXT step -- the same point in the loop where the
+ * reference's scheduler.step(total_loss) takes effect.  Learning rates are kept in fp64 like Python floats and rounded to fp32 once.
+ * The state lives in device memory (initialise it on the host and copy it; read it back for checkpoints). */
+typedef struct desmo_plateau {
+    double best;        /* +inf initially */
+    double lrs[5];      /* current learning rates (gates, phi, z, omega, period) */
+    double threshold;   /* 1e-4 */
+    double factor;      /* 0.1 */
+    double min_lr;      /* 1e-6 */
+    double eps;         /* 1e-8 */
+    int32_t num_bad;
+    int32_t patience;
+    int32_t every;      /* scheduler cadence in epochs (1: ANEU / TURB, 10: CYL) */
+    int32_t n_groups;   /* 4, or 5 for the Fourier variant */
+    int32_t reductions; /* number of LR reductions so far (diagnostic) */
+    int32_t pad;
+} desmo_plateau;
+int desmo_plateau_step(desmo_plateau* state_dev, const int32_t* step_dev, const float* losses_dev, float* hyper_dev, void* stream);
+
+/* Multi-GPU exchange over NVLink / NVSwitch PEER MEMORY instead of NCCL (replaces the
+ * torch.distributed.all_reduce a multi-GPU port of CYL:766-768 would issue on the gradients).  Every rank keeps its `red`
+ * contribution in a buffer all ranks of the node have mapped, followed by a pad of 2 * world uint32 flags (zeroed once, before the
+ * first step, with a barrier).  Per step: desmo_peer_begin_step (before the fused pass: waits until every peer has consumed this
+ * rank's previous red) ... fused pass writes this rank's red ... desmo_peer_allreduce (signals the peers, waits for theirs, adds
+ * all ranks' buffers in rank order into red_sum -- bit-identical on every rank).  Stream-ordered, CUDA-graph capturable, no host
+ * synchronisation; a peer that never arrives traps after ~10 s. */
+#define DESMO_MAX_PEERS 16
+typedef struct desmo_peer {
+    int32_t world, rank;
+    const uint64_t* red_ptrs;   /* DEVICE array [world]: address (as mapped in THIS process) of every rank's red buffer */
+    const uint64_t* flag_ptrs;  /* DEVICE array [world]: address of every rank's flag pad (uint32 ready[world], consumed[world]) */
+    uint32_t* state;            /* DEVICE, local, 2 x uint32 zero-initialised: epoch, completion counter */
+} desmo_peer;
+int desmo_peer_begin_step(const desmo_peer* p, void* stream);
+int desmo_peer_allreduce(const desmo_peer* p, int64_t count /* floats, multiple of 4 */, float* red_sum, void* stream);
+
 /* Device-resident training session fed from HOST memory (one process of the reference's loop, CYL:706-778).
  * desmo_session_step_host(snapshot_host) = `snapshot = x[0].type(FloatTensor).to(device)` (CYL:708, pass NULL to keep the
  * resident copy) + forward/loss/backward/optimizer.step (CYL:711-768) + `loss.item()` (CYL:769): losses_host[4] =

@@ -160,6 +160,35 @@ def test_training_trajectory_matches_reference_golden(name, path):
     assert np.allclose(tr.scheduler.lrs, fx["final_lrs"])
 
 
+def test_device_scheduler_is_bit_identical_to_host_scheduler():
+    """ReduceLROnPlateau inside the captured step (desmo_plateau_step) against the host scheduler (= torch's, test_cabi_cpu): the same
+    learning-rate drops at the same epochs -- overshooting step sizes with patience 2 at a cadence of 3 epochs force several within 400 steps -- hence bit-identical
+    parameters; and the golden trajectory's own schedule (no drop within its 1000 steps) is reproduced."""
+    from desmo_b200 import DesmoTrainer
+
+    fx, meta, modes, snap, prm = golden_case("traj_chan_r4p2")
+    hot = [50.0 * v for v in meta["lrs"]]  # step sizes that overshoot: the loss stalls and the scheduler has to act
+    for lrs, patience, every, steps in ((hot, 2, 3, 400), (meta["lrs"], meta["patience"], meta["sched_every"], meta["steps"])):
+        runs = []
+        for dev_sched in (False, True):
+            e = _engine(prm, modes, snap, 2)
+            tr = DesmoTrainer(e, lrs=lrs, beta=meta["beta"], l1_lambda=meta["l1_lambda"], patience=patience, sched_every=every,
+                              device_scheduler=dev_sched)
+            for _ in range(steps):
+                tr.step()
+            torch.cuda.synchronize()
+            sc = tr.sync_scheduler()
+            runs.append((engine_params(e), list(sc.lrs), sc.best, sc.num_bad, e.hyper.cpu().numpy().copy()))
+        assert runs[0][1] == runs[1][1] and runs[0][2] == runs[1][2] and runs[0][3] == runs[1][3], (runs[0][1:4], runs[1][1:4])
+        assert np.array_equal(runs[0][4], runs[1][4])
+        for k in runs[0][0]:
+            assert np.array_equal(runs[0][0][k], runs[1][0][k]), k
+        if patience == 2:
+            assert any(a != b for a, b in zip(runs[1][1], lrs)), runs[1][1]  # drops did occur
+        else:
+            assert np.allclose(runs[1][1], fx["final_lrs"])
+
+
 def test_host_buffer_entry_point_matches_oracle():
     """desmo_train_host: the whole reference loop through HOST buffers (upload, steps, download)."""
     from desmo_b200 import _lib
