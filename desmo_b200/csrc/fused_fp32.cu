@@ -277,30 +277,16 @@ __global__ void __launch_bounds__(kTile) chain_rule_kernel(const FusedArgs a, in
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long x = tile * kTile + tid;
         const bool xin = x < a.n;
-        // all global loads of the tile first, in batches of independent requests (the kernel is latency-bound otherwise: every
-        // thread reads K + 2r scattered floats): D rows of the monomials -> A_s, the trig rows and the POD modes -> registers
-        float pod[R], dtrig[3 * R];
-#pragma unroll
-        for (int i = 0; i < r; ++i) pod[i] = (x < a.ld) ? __ldg(a.P + (long long)i * a.ld + x) : 0.0f;
-#pragma unroll
-        for (int i = 0; i < r; ++i) Phi_s[i * kTile + tid] = (x < a.ld) ? __ldg(a.phi + (long long)i * a.ld + x) * pod[i] : 0.0f;
-#pragma unroll
-        for (int i = 0; i < 3 * r; ++i) dtrig[i] = xin ? __ldg(a.Dacc + (long long)(T + i) * a.ld + x) * a.scale : 0.0f;
-        for (int j0 = 0; j0 < T; j0 += 8) {
-            float v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = (xin && j0 + u < T) ? __ldg(a.Dacc + (long long)(j0 + u) * a.ld + x) : 0.0f;
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (j0 + u < T) A_s[(j0 + u) * kTile + tid] = v[u] * a.scale;
+        for (int i = 0; i < r; ++i) {
+            Phi_s[i * kTile + tid] = (x < a.ld) ? a.phi[(long long)i * a.ld + x] * a.P[(long long)i * a.ld + x] : 0.0f;
+            dPhi_s[i * kTile + tid] = 0.0f;
         }
-#pragma unroll
-        for (int i = 0; i < r; ++i) dPhi_s[i * kTile + tid] = 0.0f;
         L_s[tid] = 1.0f;
         for (int j = 1; j < T; ++j) {
             const float f = Phi_s[a.mt.last[j] * kTile + tid];
             L_s[j * kTile + tid] = (a.mt.deg[j] == 1) ? f : L_s[a.mt.parent[j] * kTile + tid] * f;
         }
+        for (int j = 0; j < T; ++j) A_s[j * kTile + tid] = xin ? a.Dacc[(long long)j * a.ld + x] * a.scale : 0.0f;
         for (int j = T - 1; j >= 1; --j) {
             const float adj = A_s[j * kTile + tid];
             const int par = a.mt.parent[j], v = a.mt.last[j];
@@ -309,13 +295,18 @@ __global__ void __launch_bounds__(kTile) chain_rule_kernel(const FusedArgs a, in
         }
 #pragma unroll
         for (int i = 0; i < r; ++i) {
-            const float ph = Phi_s[i * kTile + tid];
+            const float ph = Phi_s[i * kTile + tid], pod = (x < a.ld) ? a.P[(long long)i * a.ld + x] : 0.0f;
             const float ws = a.omega[3 * i], wc = a.omega[3 * i + 1], wh = a.omega[3 * i + 2];
-            const float ds = dtrig[i], dc = dtrig[r + i], dh = dtrig[2 * r + i];
+            float ds = 0.0f, dc = 0.0f, dh = 0.0f;
+            if (xin) {
+                ds = a.Dacc[(long long)(T + i) * a.ld + x] * a.scale;
+                dc = a.Dacc[(long long)(T + r + i) * a.ld + x] * a.scale;
+                dh = a.Dacc[(long long)(T + 2 * r + i) * a.ld + x] * a.scale;
+            }
             const float cs = cosf(ws * ph), sn = sinf(wc * ph), th = tanhf(wh * ph);
             const float sech2 = 1.0f - th * th;
             const float dphi_i = dPhi_s[i * kTile + tid] + (ds * ws * cs - dc * wc * sn + dh * wh * sech2);
-            if (x < a.ld) a.dphi[(long long)i * a.ld + x] = dphi_i * pod[i];
+            if (x < a.ld) a.dphi[(long long)i * a.ld + x] = dphi_i * pod;
             om_acc[3 * i] += ds * ph * cs;
             om_acc[3 * i + 1] -= dc * ph * sn;
             om_acc[3 * i + 2] += dh * ph * sech2;
@@ -412,10 +403,38 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
             *reinterpret_cast<float4*>(red + o) = t;
         }
     }
+    // scalars: [slot][kScal] doubles from up to ~750 CTAs.  Warp w adds the slots b = w, w + 8, ... (coalesced rows, four rows of
+    // independent loads in flight), then the eight warp sums are added in warp order: a fixed order, and ~10x less latency than one
+    // thread per scalar walking all slots.
+    __shared__ double sc_s[8][kScal];
+    if ((what & 2) && blockIdx.x == 0) {
+        double acc[3] = {0.0, 0.0, 0.0};
+        int b = w;
+        for (; b + 24 < nslots; b += 32) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int i = lane + 32 * c;
+                if (i < kScal) {
+                    const double v0 = Spart[(long long)b * kScal + i], v1 = Spart[(long long)(b + 8) * kScal + i];
+                    const double v2 = Spart[(long long)(b + 16) * kScal + i], v3 = Spart[(long long)(b + 24) * kScal + i];
+                    acc[c] = (((acc[c] + v0) + v1) + v2) + v3;
+                }
+            }
+        }
+        for (; b < nslots; b += 8)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                if (lane + 32 * c < kScal) acc[c] += Spart[(long long)b * kScal + lane + 32 * c];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            if (lane + 32 * c < kScal) sc_s[w][lane + 32 * c] = acc[c];
+        __syncthreads();
+    }
     if ((what & 2) && blockIdx.x == 0 && threadIdx.x < kScal) {
         const int i = threadIdx.x;
-        double s = 0.0;
-        for (int b = 0; b < nslots; ++b) s += Spart[(long long)b * kScal + i];
+        double s = sc_s[0][i];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) s += sc_s[k][i];
         // compact layout: [loss | gram r*r | domega 3r]
         if (i == 0) {
             red[ecount] = (float)s;

@@ -151,12 +151,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
-// One try_wait without the retry loop.  A SYNCS round trip costs several hundred cycles under this kernel's shared-memory load even
-// when the phase completed long ago; a straight-line probe lets ptxas place independent work (or a second probe) under that latency,
-// which a wait loop (a branch after every attempt) cannot.  Callers fall back to mbar_wait when the probe fails.
+// One non-blocking test of a phase, without a retry loop.  A SYNCS round trip costs a few hundred cycles under this kernel's
+// shared-memory load even when the phase completed long ago; a straight-line probe lets ptxas place independent work (or a second
+// probe) under that latency, which a wait loop (a branch after every attempt) cannot.  test_wait, not try_wait: try_wait may park the
+// warp for a system-dependent time when the phase is still open, which would stall exactly the work the probe is meant to overlap
+// (seen in the two-group experiment, profiles/README.md).  Callers fall back to mbar_wait when the probe fails.
 __device__ __forceinline__ uint32_t mbar_probe(uint32_t bar, uint32_t parity) {
     uint32_t done;
-    asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
+    asm volatile("{\n\t.reg .pred q;\n\tmbarrier.test_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done;
 }

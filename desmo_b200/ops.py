@@ -1,7 +1,7 @@
 """torch custom ops over the C ABI: one ``torch.ops.desmo_b200.*`` op per hot-path entry point of include/desmo_b200.h.
 
   build_w, fused_residual_grad, recon_backward, adamax_update, assemble_grads, reconstruct, library_colnorm2, term_norms,
-  pod_gram, pod_eig, pod_project, preprocess
+  pod_gram, pod_eig, pod_project, preprocess, plateau_step, peer_begin_step, peer_allreduce
 
 They take the packed device tensors of a DesmoEngine (layout: include/desmo_b200.h) plus the shape integers and launch the
 sm_100a kernels on the current stream.  CUDA only: no CPU implementation is registered and every op checks its tensors, so a call
@@ -160,6 +160,37 @@ def preprocess(V: torch.Tensor, U: torch.Tensor, mean: Optional[torch.Tensor], m
     with torch.cuda.device(V.device):
         check(_lib.load().desmo_preprocess(C.byref(s), _p(V), 1 if V.dtype == torch.float64 else 0, V.stride(0), m_in, t_stride, d_in, d_use,
                                            flags, _p(U), _p(mean), _stream(V)), "desmo_preprocess")
+
+
+@torch.library.custom_op("desmo_b200::plateau_step", mutates_args=("state", "hyper"))
+def plateau_step(state: torch.Tensor, step: torch.Tensor, losses: torch.Tensor, hyper: torch.Tensor) -> None:
+    """ReduceLROnPlateau.step(losses[3]) on the device (desmo_plateau_step); ``state`` is the desmo_plateau struct as bytes."""
+    _require_cuda(state, step, losses, hyper)
+    with torch.cuda.device(state.device):
+        check(_lib.load().desmo_plateau_step(_p(state), _p(step), _p(losses), _p(hyper), _stream(state)), "desmo_plateau_step")
+
+
+@torch.library.custom_op("desmo_b200::peer_begin_step", mutates_args=("peer_state",))
+def peer_begin_step(peer_tables: torch.Tensor, peer_state: torch.Tensor, world: int, rank: int) -> None:
+    """Waits (on the stream) until every peer has consumed this rank's previous ``red``.  peer_tables: int64 [2 * world] device tensor
+    (addresses of every rank's red buffer, then of every rank's flag pad); peer_state: int32 [2]."""
+    from .engine import _PeerDesc
+
+    _require_cuda(peer_tables, peer_state)
+    d = _PeerDesc(world, rank, peer_tables.data_ptr(), peer_tables.data_ptr() + 8 * world, peer_state.data_ptr())
+    with torch.cuda.device(peer_tables.device):
+        check(_lib.load().desmo_peer_begin_step(C.byref(d), _stream(peer_tables)), "desmo_peer_begin_step")
+
+
+@torch.library.custom_op("desmo_b200::peer_allreduce", mutates_args=("red_sum", "peer_state"))
+def peer_allreduce(peer_tables: torch.Tensor, peer_state: torch.Tensor, red_sum: torch.Tensor, world: int, rank: int) -> None:
+    """One-shot rank-ordered sum of every rank's peer-mapped ``red`` into red_sum (desmo_peer_allreduce)."""
+    from .engine import _PeerDesc
+
+    _require_cuda(peer_tables, peer_state, red_sum)
+    d = _PeerDesc(world, rank, peer_tables.data_ptr(), peer_tables.data_ptr() + 8 * world, peer_state.data_ptr())
+    with torch.cuda.device(peer_tables.device):
+        check(_lib.load().desmo_peer_allreduce(C.byref(d), red_sum.numel(), _p(red_sum), _stream(peer_tables)), "desmo_peer_allreduce")
 
 
 def _shape_args(e):

@@ -18,8 +18,9 @@ out = np.zeros(16384, np.uint64)
 _lib.check(e.lib.desmo_debug_timers(ctypes.byref(e.shape), e.workspace.data_ptr(), out.ctypes.data_as(ctypes.c_void_p), out.size))
 TAGS = {1: "g1:begin", 2: "g1:W_FULL ok", 3: "g1:REC_EMPTY ok", 4: "g1:GT_FULL ok", 5: "g1:issued", 6: "g34:begin", 7: "g34:R_FULL ok",
         9: "g3 issued", 10: "g4 q0 issued", 11: "g4 q1 issued", 12: "g4 q2 issued", 13: "g4 q3 issued",
-        20: "wait REC_FULL", 21: "REC_FULL ok", 22: "U_FULL ok", 23: "tmem ld done", 24: "residual done/REC_EMPTY", 25: "split done",
-        26: "R_EMPTYQ ok", 27: "R_s stored", 28: "fence+R_FULL arrive", 29: "after done", 30: "next library -> TMEM", 50: "REC_FULL completes (G1 done)", 51: "R_EMPTYQ3 completes (G4 done)"}
+        20: "wait REC_FULL", 21: "REC_FULL+U_FULL ok", 22: "tmem ld issued", 23: "tmem ld done", 24: "residual done/REC_EMPTY", 25: "split done",
+        26: "R_EMPTYQ ok", 27: "R_s stored", 28: "fence+R_FULL arrive", 29: "after done", 30: "next library -> TMEM",
+        50: "REC_FULL completes (G1 done)", 51: "R_EMPTYQ3 completes (G4 done)"}
 ROLE = ["mma", "epi q0h0", "epi q1h1", "epi q2h2", "epi q3h3", "pipe"]
 ev = []
 for log in range(6):
