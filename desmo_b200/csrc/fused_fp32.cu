@@ -267,8 +267,8 @@ __global__ void __launch_bounds__(kTile) chain_rule_kernel(const FusedArgs a, in
 #pragma unroll
     for (int i = 0; i < R * (R + 1) / 2; ++i) gr_acc[i] = 0.0f;
     float* Phi_s = fs;                         // [kMaxR][kTile]
-    float* dPhi_s = Phi_s + kMaxR * kTile;     // [kMaxR][kTile]
-    float* L_s = dPhi_s + kMaxR * kTile;       // [T][kTile]   library values
+    float* dPhi_s = Phi_s + R * kTile;         // [R][kTile]   (sized by the template's R: one more CTA per SM at r = 4)
+    float* L_s = dPhi_s + R * kTile;           // [T][kTile]   library values
     float* A_s = L_s + T * kTile;              // [T][kTile]   adjoints, start as D_j
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 8 * kScal; i += kTile) red_s[i] = 0.0;
@@ -468,7 +468,7 @@ int chain_rule_launch(const desmo_shape* s, const MonoTable& mt, int T, int Kp, 
     a.mt = mt;
     const long long ntiles = (a.ld + kTile - 1) / kTile;
     const int gc = (int)(ntiles < 592 ? ntiles : 592);
-    const size_t sm = 8 * kScal * sizeof(double) + (size_t)(2 * kMaxR + 2 * a.T) * kTile * sizeof(float);
+    const size_t sm = 8 * kScal * sizeof(double) + (size_t)(2 * a.r + 2 * a.T) * kTile * sizeof(float);
     DESMO_CUDA(chain_rule_dispatch(a, slot_base, gc, sm, st));
     *nslots = gc;
     return DESMO_OK;
@@ -511,7 +511,7 @@ static int launch_fused(const FusedArgs& a, int sms, size_t smem_cap, cudaStream
     int nslots = gx * nchunk;
     if (nchunk > 1) {
         const int gc = (int)(ntiles < 256 ? ntiles : 256);
-        const size_t sm = 8 * kScal * sizeof(double) + (size_t)(2 * kMaxR + 2 * a.T) * kTile * sizeof(float);
+        const size_t sm = 8 * kScal * sizeof(double) + (size_t)(2 * a.r + 2 * a.T) * kTile * sizeof(float);
         DESMO_CUDA(chain_rule_dispatch(b, nslots, gc, sm, st));
         nslots += gc;
     }
