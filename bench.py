@@ -62,6 +62,7 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index, self.samples, self._stop = index, [], threading.Event()  # samples: (sm_mhz, sm_max_mhz, {reasons})
         self.power_w, self.power_limit_w = [], None
+        self._ready = threading.Event()  # set after the first sample: NVML initialisation must not eat a short timed region
         self.th = threading.Thread(target=self._run, daemon=True)
         self.source = "nvml"
 
@@ -80,6 +81,7 @@ class ClockSampler:
         while not self._stop.is_set():
             mask = int(get_reasons(h))
             self.samples.append((int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(mx), {n for n, b in self.BITS if mask & b}))
+            self._ready.set()
             if k % 8 == 0:  # board power: a slow sensor, sampled every ~16 ms
                 try:
                     self.power_w.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
@@ -98,6 +100,7 @@ class ClockSampler:
                 if len(c) >= 6 and c[0].isdigit():
                     names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
                     self.samples.append((int(c[0]), int(c[1]), {n for n, v in zip(names, c[2:6]) if v.lower().startswith("active")}))
+                    self._ready.set()
             except Exception:
                 pass
             self._stop.wait(0.05)
@@ -110,6 +113,7 @@ class ClockSampler:
 
     def __enter__(self):
         self.th.start()
+        self._ready.wait(timeout=10.0)  # the sampler is running before the timed region starts
         return self
 
     def __exit__(self, *a):

@@ -142,7 +142,7 @@ int carve_workspace(const desmo_shape* s, const Dims& d, void* base, Workspace* 
     ws->Epart = reinterpret_cast<float*>(b + off);  off = align_up(off + (fused ? sizeof(float) * (size_t)sms * d.Kp * s->mld : 0), 256);
     ws->l1 = reinterpret_cast<float*>(b + off);     off = align_up(off + 256, 256);
     ws->tc = reinterpret_cast<float*>(b + off);     off = align_up(off + (fused ? sizeof(float) * 2 * (size_t)(d.Kp > 32 ? d.Kp : 32) * s->mld : 0), 256);  // >= 3 bf16 planes [32][mld]
-    ws->gram = reinterpret_cast<float*>(b + off);   off = align_up(off + sizeof(float) * (size_t)sms * 128 * 128, 256);
+    ws->gram = reinterpret_cast<float*>(b + off);   off = align_up(off + sizeof(float) * (size_t)sms * 128 * 128 + 1024, 256);  // + pace counters
     ws->Dacc = reinterpret_cast<float*>(b + off);   off = align_up(off + sizeof(float) * (size_t)d.Kp * s->ld, 256);
     off = align_up(off, 1024);
     ws->gemm = b + off;

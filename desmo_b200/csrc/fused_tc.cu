@@ -390,15 +390,16 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
             }
         } else if (lane == 2) {
             // Watchdog: a protocol error must fail the launch, not hang the GPU.  One otherwise idle lane naps and checks that the
-            // MMA issuer keeps advancing; ~1 s without progress traps.
+            // MMA issuer keeps advancing; ~2 s without progress traps.  Short naps: the CTA cannot retire before this lane has seen
+            // the last slab-tile issued (a 20 us nap cost the script-sized shapes 10-20 us per launch).
             int last = -1;
             unsigned idle = 0;
             for (;;) {
                 const int pr = progress_s;
                 if (pr >= total) break;
                 if (pr != last) { last = pr; idle = 0; }
-                else if (++idle > 50000u) __trap();
-                __nanosleep(20000);
+                else if (++idle > 2000000u) __trap();
+                __nanosleep(1000);
             }
         } else if (kDebug && lane == 1 && blockIdx.x == 0) {
             // debug timeline: when the tensor pipe's commits actually land (polled in issue order: G1(it), then G4(it - 1))

@@ -18,6 +18,7 @@ namespace gram {
 constexpr int BM = 128;            // rows (snapshots) per tile edge
 constexpr int BK = 64;             // mesh points per chunk (= one 128 B swizzled row of bf16)
 constexpr int CONV_WARPS = 8;
+constexpr int PACE = 32;           // chunks between pacing points of the CTAs that stream the same range of mesh points (see the kernel)
 constexpr int FLUSH = 16;          // chunks between accumulator flushes: the tensor core truncates when it adds into the fp32
                                    // accumulator (bias ~1e-8 per MMA), so chains are kept to 16 x 24 MMAs and summed in fp32 RN outside
 constexpr int THREADS = 128 + CONV_WARPS * 32;
@@ -75,7 +76,8 @@ __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t& w1, ui
 }
 
 __global__ void __launch_bounds__(THREADS, 1) gram_tc_kernel(const float* __restrict__ U, long long ld, int m, int ntile, long long xchunk,
-                                                             long long xtotal, float* __restrict__ C, float* __restrict__ part) {
+                                                             long long xtotal, float* __restrict__ C, float* __restrict__ part,
+                                                             unsigned* __restrict__ pace) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[8];
     __shared__ uint32_t tmem_base_s;
@@ -181,6 +183,21 @@ __global__ void __launch_bounds__(THREADS, 1) gram_tc_kernel(const float* __rest
         if (nchunks > 0) load_chunk(0);
         for (int c = 0; c < nchunks; ++c) {
             const int st = c & 1;
+            if (c > 0 && c % PACE == 0) {
+                // Pacing: the gridDim.x tiles of one point range read the same rows of U (every 128-row block is an operand of
+                // several tiles); they only share them through L2 while they stay within an L2-sized window of each other, and left
+                // alone they drift apart (ncu: 25 GB of DRAM reads for 12.6 GB of data).  Every PACE chunks (a window of PACE * 64
+                // points x m rows x 4 ranges = 33 MB) a CTA announces itself and waits -- briefly, with a time limit, so that it
+                // is a hint and never a deadlock -- until the others of its range have arrived.
+                if (tid == 128) {
+                    const unsigned target = (unsigned)gridDim.x * (unsigned)(c / PACE);
+                    __threadfence();
+                    atomicAdd(pace + blockIdx.y, 1u);
+                    const long long t0 = clock64();
+                    while (*reinterpret_cast<volatile unsigned*>(pace + blockIdx.y) < target && clock64() - t0 < 40000) __nanosleep(100);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(CONV_WARPS * 32) : "memory");
+            }
             if (c >= 2) mbar_wait(bar(EMPTY0 + st), ((c >> 1) - 1) & 1);
             store_planes(sbase + st * STAGE, ra);
             if (!diag) store_planes(sbase + st * STAGE + OPERAND, rb);
@@ -259,8 +276,10 @@ int pod_gram_tc(const desmo_shape* s, const float* U, float* C, void* workspace,
     long long xchunk = ((xtotal + nsplit - 1) / nsplit + BK - 1) / BK * BK;
     nsplit = (xtotal + xchunk - 1) / xchunk;
     DESMO_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    if ((long long)npairs * nsplit > sms) return DESMO_ERR_UNSUPPORTED;  // one partial tile per SM in the workspace
-    gram_tc_kernel<<<dim3(npairs, (unsigned)nsplit), THREADS, SMEM_BYTES, st>>>(U, s->ld, m, ntile, xchunk, xtotal, C, part);
+    if ((long long)npairs * nsplit > sms || nsplit > 256) return DESMO_ERR_UNSUPPORTED;  // one partial tile per SM in the workspace
+    unsigned* pace = reinterpret_cast<unsigned*>(part + (size_t)sms * BM * BM);            // pacing counters, one per point range
+    DESMO_CUDA(cudaMemsetAsync(pace, 0, 1024, st));
+    gram_tc_kernel<<<dim3(npairs, (unsigned)nsplit), THREADS, SMEM_BYTES, st>>>(U, s->ld, m, ntile, xchunk, xtotal, C, part, pace);
     DESMO_CUDA(cudaGetLastError());
     gram_reduce_kernel<<<npairs, 256, 0, st>>>(part, npairs, (int)nsplit, m, ntile, C);
     DESMO_CUDA(cudaGetLastError());
