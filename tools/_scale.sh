@@ -10,4 +10,4 @@ import json; d=json.load(open('gpurun_out/scale_$1_n$N.json')); print('$1 N=$N',
 }
 run weak ""
 run strong20 "--scaling strong --total-points $((3*1048576))"
-run strong23 "--scaling strong --total-points $((3*8388608))"
+[ -z "$SKIP23" ] && run strong23 "--scaling strong --total-points $((3*8388608))"
