@@ -21,14 +21,14 @@ _lib.check(e.lib.desmo_debug_timers(ctypes.byref(e.shape), e.workspace.data_ptr(
 t = out[:148 * 32].reshape(148, 32).astype(np.float64)
 nst = n / 128 / 148 * 8
 names = ["mma:wait W_FULL", "mma:wait REC_EMPTY", "mma:wait GT_FULL", "mma:wait R_FULL", "mma:wait D_EMPTY", "", "", "",
-         "epi:wait REC_FULL", "epi:phase A", "epi:wait R_EMPTY", "epi:after R_FULL (D drain / next library terms)", "epi:  R_s stores", "", "epi:next tile's TMEM library store", "epi:  fence + arrive R_FULL", "epi:total",
-         "", "", "", "prod0:wait U_EMPTY", "prod0:total", "prod1:wait U_EMPTY", "prod1:total",
+         "epi:wait REC_FULL + U_FULL (probed together)", "epi:phase A (tcgen05.ld, residual, split)", "epi:wait R_EMPTY", "epi:after R_FULL (D drain / next library terms)", "epi:  R_s stores", "", "epi:next tile's TMEM library store", "epi:  fence + arrive R_FULL", "epi:total",
+         "", "", "", "prodU(warp 2):wait U_EMPTY", "prodU(warp 2):total", "prodU(warp 3):wait U_EMPTY", "prodU(warp 3):total",
          "epi:wait LAT_FULL", "epi:library terms"]
 for i, nm in enumerate(names):
     if nm:
         print(f"{nm:48s} mean {t[:, i].mean() / nst:9.0f} cycles/slab-tile   (min {t[:, i].min() / nst:8.0f}, max {t[:, i].max() / nst:8.0f})")
 
 w = out[8192:8192 + 128].reshape(16, 8).astype(np.float64) / nst
-print("per-warp (CTA 0)  e: q h | wait REC_FULL | phase A (of which U_FULL) | wait R_EMPTY | after | TMEM lib")
+print("per-warp (CTA 0)  e: q h | wait REC+U | phase A (-) | wait R_EMPTY | after | TMEM lib")
 for e_ in range(16):
     print(f"  warp {e_:2d}: q{e_ & 3} h{e_ >> 2} | {w[e_,0]:7.0f} | {w[e_,1]:7.0f} ({w[e_,4]:5.0f}) | {w[e_,2]:6.0f} | {w[e_,3]:6.0f} | {w[e_,6]:5.0f}")
