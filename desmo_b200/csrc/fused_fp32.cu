@@ -30,6 +30,7 @@ struct FusedArgs {
     float* Dacc;
     long long n, ld;
     int m, mld, r, T, K, nchunk, mc;
+    int cr_stages;  // chain rule: 2 = the next tile's rows are in flight while a tile is processed, 1 = when two stages do not fit
     float scale;  // 2 / (n_global * m)
     float seed_scale;  // > 0: U holds dL/drecon and R := seed_scale * U instead of G W - U (desmo_recon_backward)
     MonoTable mt;
@@ -252,13 +253,20 @@ __global__ void __launch_bounds__(kTile, 1) fused_fp32_kernel(const FusedArgs a)
 // tensor-core path.  The monomial part is ONE reverse sweep over the library: with L_j = L_parent(j) * Phi_last(j) (exactly the
 // left-to-right products of POOL_DATA, CYL:390-431), adj(L_parent) += adj(L_j) * Phi_last and dPhi_last += adj(L_j) * L_parent --
 // two FMAs per term instead of a product per (term, position).
+// Memory-level parallelism: every thread needs K + 2r scattered floats per point (the D rows, phi, P) and the kernel is latency-bound
+// if they are requested where they are used.  All rows of the NEXT tile are therefore requested with cp.async (no registers, straight
+// into the other half of a double buffer) before the current tile is processed: ~35 loads per thread stay in flight across a tile's
+// arithmetic (2 CTAs per SM x 256 threads x 35 x 4 B = 72 KB per SM).
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
 template <int R>
 __global__ void __launch_bounds__(kTile) chain_rule_kernel(const FusedArgs a, int slot_base) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* red_s = reinterpret_cast<double*>(smem_raw);
     float* fs = reinterpret_cast<float*>(smem_raw + 8 * kScal * sizeof(double));
     constexpr int r = R;
-    const int T = a.T;
+    const int T = a.T, K = T + 3 * r;
     // per-thread partial sums over all tiles of this CTA (registers; R is a template parameter so that they stay there):
     // d omega [3R] and the upper triangle of Phi^T Phi; reduced across the CTA once, after the tile loop
     float om_acc[3 * R], gr_acc[R * (R + 1) / 2];
@@ -266,19 +274,49 @@ __global__ void __launch_bounds__(kTile) chain_rule_kernel(const FusedArgs a, in
     for (int i = 0; i < 3 * R; ++i) om_acc[i] = 0.0f;
 #pragma unroll
     for (int i = 0; i < R * (R + 1) / 2; ++i) gr_acc[i] = 0.0f;
-    float* Phi_s = fs;                         // [kMaxR][kTile]
-    float* dPhi_s = Phi_s + R * kTile;         // [R][kTile]   (sized by the template's R: one more CTA per SM at r = 4)
-    float* L_s = dPhi_s + R * kTile;           // [T][kTile]   library values
-    float* A_s = L_s + T * kTile;              // [T][kTile]   adjoints, start as D_j
+    const int stage_floats = (K + 2 * r) * kTile;  // staged per tile: D rows [K], phi [r], P [r]
+    float* stage0 = fs;                            // [2][K + 2r][kTile]
+    const int nst = a.cr_stages;
+    float* Phi_s = fs + nst * stage_floats;        // [R][kTile]
+    float* dPhi_s = Phi_s + R * kTile;             // [R][kTile]
+    float* L_s = dPhi_s + R * kTile;               // [T][kTile]   library values
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 8 * kScal; i += kTile) red_s[i] = 0.0;
-    __syncthreads();
     const long long ntiles = (a.ld + kTile - 1) / kTile;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    auto request = [&](long long tile, int buf) {  // rows of `tile` -> stage `buf`; points beyond ld are skipped (their slots are unused)
         const long long x = tile * kTile + tid;
-        const bool xin = x < a.n;
+        float* st = stage0 + buf * stage_floats + tid;
+        if (x < a.ld) {
+            for (int j = 0; j < K; ++j) cp_async4(st + j * kTile, a.Dacc + (long long)j * a.ld + x);
+#pragma unroll
+            for (int i = 0; i < r; ++i) {
+                cp_async4(st + (K + i) * kTile, a.phi + (long long)i * a.ld + x);
+                cp_async4(st + (K + r + i) * kTile, a.P + (long long)i * a.ld + x);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (nst == 2 && (long long)blockIdx.x < ntiles) request(blockIdx.x, 0);
+    __syncthreads();
+    int buf = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= (nst - 1)) {
+        const long long x = tile * kTile + tid;
+        const bool xin = x < a.n, xld = x < a.ld;
+        if (nst == 2 && tile + gridDim.x < ntiles) {
+            request(tile + gridDim.x, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            if (nst == 1) request(tile, 0);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        // each thread reads only what it requested itself: no barrier needed
+        const float* A_in = stage0 + buf * stage_floats + tid;   // D rows of this point (raw, unscaled)
+        float* A_s = stage0 + buf * stage_floats;                // reused in place as the adjoints
+        float pod[R];
+#pragma unroll
         for (int i = 0; i < r; ++i) {
-            Phi_s[i * kTile + tid] = (x < a.ld) ? a.phi[(long long)i * a.ld + x] * a.P[(long long)i * a.ld + x] : 0.0f;
+            pod[i] = xld ? A_in[(K + r + i) * kTile] : 0.0f;
+            Phi_s[i * kTile + tid] = xld ? A_in[(K + i) * kTile] * pod[i] : 0.0f;
             dPhi_s[i * kTile + tid] = 0.0f;
         }
         L_s[tid] = 1.0f;
@@ -286,7 +324,7 @@ __global__ void __launch_bounds__(kTile) chain_rule_kernel(const FusedArgs a, in
             const float f = Phi_s[a.mt.last[j] * kTile + tid];
             L_s[j * kTile + tid] = (a.mt.deg[j] == 1) ? f : L_s[a.mt.parent[j] * kTile + tid] * f;
         }
-        for (int j = 0; j < T; ++j) A_s[j * kTile + tid] = xin ? a.Dacc[(long long)j * a.ld + x] * a.scale : 0.0f;
+        for (int j = 0; j < T; ++j) A_s[j * kTile + tid] = xin ? A_in[j * kTile] * a.scale : 0.0f;
         for (int j = T - 1; j >= 1; --j) {
             const float adj = A_s[j * kTile + tid];
             const int par = a.mt.parent[j], v = a.mt.last[j];
@@ -295,18 +333,18 @@ __global__ void __launch_bounds__(kTile) chain_rule_kernel(const FusedArgs a, in
         }
 #pragma unroll
         for (int i = 0; i < r; ++i) {
-            const float ph = Phi_s[i * kTile + tid], pod = (x < a.ld) ? a.P[(long long)i * a.ld + x] : 0.0f;
+            const float ph = Phi_s[i * kTile + tid];
             const float ws = a.omega[3 * i], wc = a.omega[3 * i + 1], wh = a.omega[3 * i + 2];
             float ds = 0.0f, dc = 0.0f, dh = 0.0f;
             if (xin) {
-                ds = a.Dacc[(long long)(T + i) * a.ld + x] * a.scale;
-                dc = a.Dacc[(long long)(T + r + i) * a.ld + x] * a.scale;
-                dh = a.Dacc[(long long)(T + 2 * r + i) * a.ld + x] * a.scale;
+                ds = A_in[(T + i) * kTile] * a.scale;
+                dc = A_in[(T + r + i) * kTile] * a.scale;
+                dh = A_in[(T + 2 * r + i) * kTile] * a.scale;
             }
             const float cs = cosf(ws * ph), sn = sinf(wc * ph), th = tanhf(wh * ph);
             const float sech2 = 1.0f - th * th;
             const float dphi_i = dPhi_s[i * kTile + tid] + (ds * ws * cs - dc * wc * sn + dh * wh * sech2);
-            if (x < a.ld) a.dphi[(long long)i * a.ld + x] = dphi_i * pod;
+            if (xld) a.dphi[(long long)i * a.ld + x] = dphi_i * pod[i];
             om_acc[3 * i] += ds * ph * cs;
             om_acc[3 * i + 1] -= dc * ph * sn;
             om_acc[3 * i + 2] += dh * ph * sech2;
@@ -341,7 +379,6 @@ __global__ void __launch_bounds__(kTile) chain_rule_kernel(const FusedArgs a, in
         a.Spart[(long long)(slot_base + blockIdx.x) * kScal + i] = s;
     }
 }
-
 // chain_rule_kernel<R> for R = a.r (1..kMaxR)
 template <int R>
 static cudaError_t chain_rule_go(const FusedArgs& a, int slot_base, int gc, size_t sm, cudaStream_t st) {
@@ -350,7 +387,13 @@ static cudaError_t chain_rule_go(const FusedArgs& a, int slot_base, int gc, size
     chain_rule_kernel<R><<<gc, kTile, sm, st>>>(a, slot_base);
     return cudaGetLastError();
 }
-static cudaError_t chain_rule_dispatch(const FusedArgs& a, int slot_base, int gc, size_t sm, cudaStream_t st) {
+static size_t chain_rule_smem(const FusedArgs& a, int stages) {
+    return 8 * kScal * sizeof(double) + (size_t)(stages * (a.T + 5 * a.r) + 2 * a.r + a.T) * kTile * sizeof(float);
+}
+static cudaError_t chain_rule_dispatch(const FusedArgs& a0, int slot_base, int gc, size_t, cudaStream_t st) {
+    FusedArgs a = a0;
+    a.cr_stages = chain_rule_smem(a0, 2) <= 110 * 1024 ? 2 : 1;  // two CTAs per SM with both stages, else one stage
+    const size_t sm = chain_rule_smem(a, a.cr_stages);
     switch (a.r) {
         case 1: return chain_rule_go<1>(a, slot_base, gc, sm, st);
         case 2: return chain_rule_go<2>(a, slot_base, gc, sm, st);
@@ -467,9 +510,8 @@ int chain_rule_launch(const desmo_shape* s, const MonoTable& mt, int T, int Kp, 
     a.scale = (float)(2.0 / ((double)s->n_global * (double)s->m));
     a.mt = mt;
     const long long ntiles = (a.ld + kTile - 1) / kTile;
-    const int gc = (int)(ntiles < 592 ? ntiles : 592);
-    const size_t sm = 8 * kScal * sizeof(double) + (size_t)(2 * a.r + 2 * a.T) * kTile * sizeof(float);
-    DESMO_CUDA(chain_rule_dispatch(a, slot_base, gc, sm, st));
+    const int gc = (int)(ntiles < 296 ? ntiles : 296);  // persistent: two CTAs per SM
+    DESMO_CUDA(chain_rule_dispatch(a, slot_base, gc, 0, st));
     *nslots = gc;
     return DESMO_OK;
 }
@@ -511,8 +553,7 @@ static int launch_fused(const FusedArgs& a, int sms, size_t smem_cap, cudaStream
     int nslots = gx * nchunk;
     if (nchunk > 1) {
         const int gc = (int)(ntiles < 256 ? ntiles : 256);
-        const size_t sm = 8 * kScal * sizeof(double) + (size_t)(2 * a.r + 2 * a.T) * kTile * sizeof(float);
-        DESMO_CUDA(chain_rule_dispatch(b, nslots, gc, sm, st));
+        DESMO_CUDA(chain_rule_dispatch(b, nslots, gc, 0, st));
         nslots += gc;
     }
     *gx_out = gx;
