@@ -80,3 +80,33 @@ def test_plateau_scheduler_matches_torch():
         ref.step(metric)
         mine.step(metric)
         assert np.allclose(mine.lrs, [g["lr"] for g in opt.param_groups], rtol=1e-12), it
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of desmo_shape / desmo_plateau / desmo_peer have the header's sizes and field offsets (checked by compiling the
+    header with the C compiler): a silent ABI drift between include/desmo_b200.h and the Python binding would corrupt launches."""
+    import os
+    import shutil
+    import subprocess
+
+    from desmo_b200.engine import _PeerDesc
+    from desmo_b200.trainer import _PlateauState
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "desmo_b200.h"\n'
+                   'int main(void) {\n'
+                   '  printf("shape %zu %zu %zu %zu %zu\\n", sizeof(desmo_shape), offsetof(desmo_shape, n_global), offsetof(desmo_shape, m), offsetof(desmo_shape, nF), offsetof(desmo_shape, path));\n'
+                   '  printf("plateau %zu %zu %zu %zu %zu %zu\\n", sizeof(desmo_plateau), offsetof(desmo_plateau, lrs), offsetof(desmo_plateau, threshold), offsetof(desmo_plateau, num_bad), offsetof(desmo_plateau, every), offsetof(desmo_plateau, reductions));\n'
+                   '  printf("peer %zu %zu %zu %zu\\n", sizeof(desmo_peer), offsetof(desmo_peer, red_ptrs), offsetof(desmo_peer, flag_ptrs), offsetof(desmo_peer, state));\n'
+                   '  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run([cc, "-std=c99", "-I", inc, str(src), "-o", str(exe)], check=True)
+    out = dict((ln.split()[0], [int(v) for v in ln.split()[1:]]) for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    S, P, Q = _lib.Shape, _PlateauState, _PeerDesc
+    assert out["shape"] == [ctypes.sizeof(S), S.n_global.offset, S.m.offset, S.nF.offset, S.path.offset]
+    assert out["plateau"] == [ctypes.sizeof(P), P.lrs.offset, P.threshold.offset, P.num_bad.offset, P.every.offset, P.reductions.offset]
+    assert out["peer"] == [ctypes.sizeof(Q), Q.red_ptrs.offset, Q.flag_ptrs.offset, Q.state.offset]
