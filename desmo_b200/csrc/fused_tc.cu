@@ -163,12 +163,6 @@ __device__ __forceinline__ uint32_t mbar_probe(uint32_t bar, uint32_t parity) {
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done;
 }
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking probe
-    uint32_t done;
-    asm volatile("{\n\t.reg .pred q;\n\tmbarrier.test_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    return done != 0;
-}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -365,29 +359,25 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
         // ======================== TMA producer: W slab planes; phi / P rows of the tile whose library is evaluated next ========================
         if (elect_one_sync()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmPhi) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
-            int lat_k = 0;  // next tile (CTA-local index) whose phi / P rows are requested; one buffer, released by the epilogue (LAT_EMPTY)
-            auto lat_issue = [&]() {
-                const int x0 = (int)((blockIdx.x + (long long)lat_k * gridDim.x) * BP);
-                mbar_expect_tx(bar(LAT_FULL), 2u * a.r * BP * 4u);
-                tma_load_2d(sbase + LAT_OFF, &tmPhi, x0, 0, bar(LAT_FULL));
-                tma_load_2d(sbase + LAT_OFF + LAT_HALF, &tmP, x0, 0, bar(LAT_FULL));
-                ++lat_k;
-            };
-            if (my_tiles > 0) lat_issue();
             for (int it = 0; it < total; ++it) {
                 const int buf = it & 1, slab = it % nslab;
-                // polled, never waited for here: the W slabs must not queue behind the epilogue's progress through the library
-                if (lat_k < my_tiles && mbar_test(bar(LAT_EMPTY), (lat_k - 1) & 1)) lat_issue();
                 if (it >= 2) mbar_wait(bar(W_EMPTY0 + buf), ((it >> 1) & 1) ^ 1, 1, it);
                 mbar_expect_tx(bar(W_FULL0 + buf), W_SLAB);
                 for (int h = 0; h < 2; ++h)
                     tma_load_2d(sbase + W_OFF + buf * W_SLAB + h * W_BOX, &tmW, slab * BT + h * 64, 0, bar(W_FULL0 + buf));
             }
-            while (lat_k < my_tiles) {
-                mbar_wait(bar(LAT_EMPTY), (lat_k - 1) & 1, 13, lat_k);
-                lat_issue();
+        } else if (lane == 3) {
+            // phi / P rows of the tile whose library is evaluated next: one buffer, refilled as soon as the epilogue has released it
+            // (LAT_EMPTY).  A lane of its own: the W loop above blocks on W_EMPTY, which (with one slab per tile) the MMA issuer
+            // only commits after the next tile's first G1 -- which needs these rows.  Found by the watchdog on a 40000 x 100 case.
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmPhi) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
+            for (int k = 0; k < my_tiles; ++k) {
+                if (k > 0) mbar_wait(bar(LAT_EMPTY), (k - 1) & 1, 13, k);
+                const int x0 = (int)((blockIdx.x + (long long)k * gridDim.x) * BP);
+                mbar_expect_tx(bar(LAT_FULL), 2u * a.r * BP * 4u);
+                tma_load_2d(sbase + LAT_OFF, &tmPhi, x0, 0, bar(LAT_FULL));
+                tma_load_2d(sbase + LAT_OFF + LAT_HALF, &tmP, x0, 0, bar(LAT_FULL));
             }
         } else if (lane == 2) {
             // Watchdog: a protocol error must fail the launch, not hang the GPU.  One otherwise idle lane naps and checks that the

@@ -113,6 +113,8 @@ CASES = [  # (kind, n, m, r, p, nF) -- ragged sizes, single tile, multi tile, ch
     ("channel", 20000, 300, 16, 1, 6),      # r = 16 Fourier, p = 1: K = 65; two chunks of points (partial sums accumulate over chunks)
     ("channel", 2000, 130, 64, 1, None),    # r = 64 (the sweep's largest mode count), p = 1: K = 257
     ("cylinder", 900, 2100, 4, 2, None),    # more than 1024 snapshots: beyond the fused kernel's TMEM budget
+    ("aneurysm", 40000, 100, 4, 2, None),   # several tiles per CTA with ONE slab each: the next tile's library is evaluated at once
+    ("aneurysm", 40000, 200, 3, 2, None),   # ... with two slabs (all of the next row in the first slab's slack), r = 3, ragged slab
 ]
 
 
