@@ -115,6 +115,8 @@ CASES = [  # (kind, n, m, r, p, nF) -- ragged sizes, single tile, multi tile, ch
     ("cylinder", 900, 2100, 4, 2, None),    # more than 1024 snapshots: beyond the fused kernel's TMEM budget
     ("aneurysm", 40000, 100, 4, 2, None),   # several tiles per CTA with ONE slab each: the next tile's library is evaluated at once
     ("aneurysm", 40000, 200, 3, 2, None),   # ... with two slabs (all of the next row in the first slab's slack), r = 3, ragged slab
+    ("cylinder", 3000, 300, 7, 1, None),    # r = 7, p = 1: K = 29, the most modes the fused kernel takes (7-row phi / P boxes)
+    ("cylinder", 1000, 50, 1, 2, None),     # a single mode: K = 6
 ]
 
 
