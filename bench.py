@@ -390,6 +390,14 @@ def main():
         trainer.step()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    have_dom = e.path_used in (_lib.PATH_FP32, _lib.PATH_TC)  # the fused kernels are bracketed by CUDA events inside the library
+    gk = ctypes.c_float(0.0)
+    graph_samples = []  # dominant kernel inside replays of the captured step (external event nodes of the graph)
+
+    def sample_graph_kernel():
+        if have_dom and e.lib.desmo_graph_fused_kernel_ms(ctypes.byref(gk)) == 0:
+            graph_samples.append(float(gk.value))
+
     with ClockSampler(local_rank) as clk:
         barrier()
         if l2_flush is None:
@@ -399,6 +407,11 @@ def main():
             ev1.record()
             barrier()
             ms_total = ev0.elapsed_time(ev1)
+            sample_graph_kernel()  # the last step of the timed region
+            for _ in range(4):     # and the last step of four more back-to-back bursts (a replay after an idle gap runs slower)
+                for _ in range(4):
+                    trainer.step()
+                sample_graph_kernel()
         else:
             ms_total = 0.0
             for _ in range(args.steps):
@@ -408,28 +421,36 @@ def main():
                 ev1.record()
                 torch.cuda.synchronize()
                 ms_total += ev0.elapsed_time(ev1)
+                sample_graph_kernel()
             barrier()
-        # dominant kernel alone: average launch duration of the fused residual+grad pass on its launching stream
+        # the fused call (dominant kernel + chain rule + partial reduction) and the dominant kernel alone in EAGER launches issued back
+        # to back (no host synchronisation between launches); kernel events are recorded inside the library on the launching stream
         e.build_w(False)
         torch.cuda.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kms = 0.0      # the fused call (dominant kernel + chain rule + partial reduction), torch events on the current stream
-        kms_dom = 0.0  # the dominant kernel alone, CUDA events recorded inside the library on the launching stream (fused kernels only)
-        dom = ctypes.c_float(0.0)
-        have_dom = e.path_used in (_lib.PATH_FP32, _lib.PATH_TC)
-        for _ in range(args.steps):
+        n_eager = max(1, min(args.steps, 64))
+        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_eager)]
+        e.lib.desmo_fused_kernel_ms_mean(None, None, 1)  # start a new series
+        for k0, k1 in pairs:
             if l2_flush is not None:
                 l2_flush.fill_(1)
             k0.record()
             e.fused_residual_grad()
             k1.record()
-            torch.cuda.synchronize()
-            kms += k0.elapsed_time(k1)
-            if have_dom:
-                _lib.check(e.lib.desmo_last_fused_kernel_ms(ctypes.byref(dom)), "desmo_last_fused_kernel_ms")
-                kms_dom += dom.value
-        kms /= args.steps
-        kms_dom = kms_dom / args.steps if have_dom else kms
+        torch.cuda.synchronize()
+        kms = sum(k0.elapsed_time(k1) for k0, k1 in pairs) / n_eager
+        kms_eager = None
+        if have_dom:
+            dom, cnt = ctypes.c_float(0.0), ctypes.c_int32(0)
+            _lib.check(e.lib.desmo_fused_kernel_ms_mean(ctypes.byref(dom), ctypes.byref(cnt), 1), "desmo_fused_kernel_ms_mean")
+            kms_eager = float(dom.value)
+        if graph_samples:
+            kms_dom, kms_src = sum(graph_samples) / len(graph_samples), (
+                f"CUDA events around the kernel inside the captured step (external event nodes), mean of {len(graph_samples)} replays: "
+                + ("the last step of the timed region and of four further 4-step bursts" if l2_flush is None else "every timed step"))
+        elif kms_eager is not None:
+            kms_dom, kms_src = kms_eager, f"CUDA events around the kernel, {n_eager} eager launches back to back"
+        else:
+            kms_dom, kms_src = kms, "the whole fused call (torch events)"
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -492,7 +513,9 @@ def main():
         achieved = alg_bytes / (kms_dom * 1e-3) / 1e9
         kernel_name = {1: "fused_fp32_kernel", 2: "fused_tc_kernel", 3: "gemm_planes_kernel x3 per chunk (GEMM path, whole fused call)"}[e.path_used]
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": kernel_name, "kernel_ms": kms_dom, "fused_call_ms": kms, "peak_source": peak_src, "algorithmic_bytes": alg_bytes}
+                "kernel": kernel_name, "kernel_ms": kms_dom, "kernel_ms_source": kms_src, "kernel_ms_eager_back_to_back": kms_eager,
+                "kernel_ms_graph_samples": [round(v, 4) for v in graph_samples], "fused_call_ms": kms, "peak_source": peak_src,
+                "algorithmic_bytes": alg_bytes}
         if e.path_used == _lib.PATH_GEMM:
             # K > 32: 6 K n m flop on 4 n m bytes -- bound by the tensor pipe; report both roofs, name the binding one
             flop_alg = 6.0 * e.K * n * m

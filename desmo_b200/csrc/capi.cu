@@ -359,6 +359,21 @@ int desmo_last_fused_kernel_ms(float* ms) {
     return rc;
 }
 
+int desmo_fused_kernel_ms_mean(float* mean_ms, int32_t* launches, int32_t reset) {
+    int n = 0;
+    const int rc = fused_event_mean_ms(mean_ms, &n, reset);
+    if (launches) *launches = n;
+    if (rc) set_error("desmo_fused_kernel_ms_mean: CUDA event query failed");
+    return rc;
+}
+
+int desmo_graph_fused_kernel_ms(float* ms) {
+    if (!ms) { set_error("desmo_graph_fused_kernel_ms: null"); return DESMO_ERR_ARG; }
+    const int rc = fused_event_graph_ms(ms);
+    if (rc) set_error("desmo_graph_fused_kernel_ms: no captured launch was timed (DESMO_KERNEL_EVENTS=1 and one eager call before the capture)");
+    return rc;
+}
+
 int desmo_debug_timers(const desmo_shape* s, void* workspace, uint64_t* out_host, int32_t count) {
     (void)s; (void)workspace;
     if (!out_host || count < 1) { set_error("desmo_debug_timers: bad argument"); return DESMO_ERR_ARG; }

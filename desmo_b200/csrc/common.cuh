@@ -85,6 +85,8 @@ int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const flo
 int fused_tc_supported(const desmo_shape* s, int Kp);
 int tc_debug_read(uint64_t* out, int count);
 int fused_event_ms(float* ms);
+int fused_event_mean_ms(float* mean_ms, int* launches, int reset);
+int fused_event_graph_ms(float* ms);
 void fused_event_record(int which, cudaStream_t st);
 int launch_update(const UpdateArgs& a, cudaStream_t st);
 int launch_plateau(desmo_plateau* st, const int32_t* step_dev, const float* losses, float* hyper, cudaStream_t stream);

@@ -9,6 +9,8 @@
 // After the last slab the chain rule through POOL_DATA / sin / cos / tanh / (phi * POD) is applied in place (single
 // chunk) or d is accumulated to Dacc for the chain-rule kernel (chunked time axis, large K*m).
 #include <algorithm>
+#include <cstdlib>
+#include <utility>
 
 #include "common.cuh"
 
@@ -379,6 +381,188 @@ __global__ void __launch_bounds__(kTile) chain_rule_kernel(const FusedArgs a, in
         a.Spart[(long long)(slot_base + blockIdx.x) * kScal + i] = s;
     }
 }
+// ---- register-resident chain rule for the common small libraries ------------------------------------------------------------
+// The kernel above walks the monomial table with run-time indices, so every value lives in shared memory and each step of the
+// sweep is a dependent shared-memory round trip: at the headline shape it is latency-bound (210 us for 441 MB).  For a library known
+// at compile time the table folds into the instruction stream: D row, library values and adjoints stay in registers, the K + 2r
+// loads of a point are issued up front, the sweep is straight-line FMAs in the SAME order as above.  The table is generated at
+// compile time by the enumeration of build_mono_table (capi.cu) and compared with the run-time table on the host before the launch.
+template <int R, int P>
+struct CtMono {
+    static constexpr int count() {
+        int t = 0;
+        for (int k = 0; k <= P; ++k) {
+            long long v = 1;
+            for (int i = 1; i <= k; ++i) v = v * (R - 1 + i) / i;
+            t += (int)v;
+        }
+        return t;
+    }
+    static constexpr int T = count();
+    int parent[T];
+    int last[T];
+    int deg[T];
+    constexpr CtMono() : parent{}, last{}, deg{} {
+        int idxs[T][P > 0 ? P : 1] = {};
+        int j = 1;
+        for (int d = 1; d <= P; ++d) {
+            int idx[P > 0 ? P : 1] = {};
+            while (true) {
+                deg[j] = d;
+                for (int q = 0; q < d; ++q) idxs[j][q] = idx[q];
+                ++j;
+                int q = d - 1;
+                while (q >= 0 && idx[q] == R - 1) --q;
+                if (q < 0) break;
+                const int v = idx[q] + 1;
+                for (int w = q; w < d; ++w) idx[w] = v;
+            }
+        }
+        for (int t = 0; t < T; ++t) {
+            const int dg = deg[t];
+            last[t] = dg ? idxs[t][dg - 1] : 0;
+            if (dg <= 1) continue;
+            for (int u = 0; u < t; ++u) {
+                if (deg[u] != dg - 1) continue;
+                bool same = true;
+                for (int q = 0; q < dg - 1; ++q) same = same && (idxs[u][q] == idxs[t][q]);
+                if (same) { parent[t] = u; break; }
+            }
+        }
+    }
+};
+template <int R, int P>
+inline constexpr CtMono<R, P> kCtMono{};
+
+template <int... Is, class F>
+__device__ __forceinline__ void static_for_impl(std::integer_sequence<int, Is...>, F&& f) {
+    (f(std::integral_constant<int, Is>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    static_for_impl(std::make_integer_sequence<int, N>{}, f);
+}
+
+constexpr int kCrTile = 128;  // points per CTA tile == threads (ld is a multiple of 128)
+template <int R, int P>
+__global__ void __launch_bounds__(kCrTile, 4) chain_rule_reg_kernel(const FusedArgs a, int slot_base) {
+    constexpr int T = CtMono<R, P>::T, K = T + 3 * R, NG = R * (R + 1) / 2, NS = 3 * R + NG;
+    __shared__ double red_s[kCrTile / 32][NS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float om_acc[3 * R], gr_acc[NG];
+#pragma unroll
+    for (int i = 0; i < 3 * R; ++i) om_acc[i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NG; ++i) gr_acc[i] = 0.0f;
+    const long long ntiles = a.ld / kCrTile;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long x = tile * kCrTile + tid;
+        const bool xin = x < a.n;
+        float A[K], ph[R], pod[R];
+#pragma unroll
+        for (int j = 0; j < K; ++j) A[j] = __ldcs(a.Dacc + (long long)j * a.ld + x);  // D is read exactly once
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            ph[i] = __ldg(a.phi + (long long)i * a.ld + x);
+            pod[i] = __ldg(a.P + (long long)i * a.ld + x);
+        }
+        float Phi[R], dPhi[R], L[T];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            Phi[i] = ph[i] * pod[i];
+            dPhi[i] = 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) A[j] = xin ? A[j] * a.scale : 0.0f;
+        L[0] = 1.0f;
+        static_for<T - 1>([&](auto jc) {
+            constexpr int j = decltype(jc)::value + 1;
+            constexpr int par = kCtMono<R, P>.parent[j], v = kCtMono<R, P>.last[j], dg = kCtMono<R, P>.deg[j];
+            if constexpr (dg == 1) L[j] = Phi[v];
+            else L[j] = L[par] * Phi[v];
+        });
+        static_for<T - 1>([&](auto jc) {
+            constexpr int j = T - 1 - decltype(jc)::value;
+            constexpr int par = kCtMono<R, P>.parent[j], v = kCtMono<R, P>.last[j];
+            const float adj = A[j];
+            dPhi[v] = fmaf(adj, L[par], dPhi[v]);
+            if constexpr (par > 0) A[par] = fmaf(adj, Phi[v], A[par]);
+        });
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const float p_i = Phi[i];
+            const float ws = a.omega[3 * i], wc = a.omega[3 * i + 1], wh = a.omega[3 * i + 2];
+            const float ds = A[T + i], dc = A[T + R + i], dh = A[T + 2 * R + i];
+            const float cs = cosf(ws * p_i), sn = sinf(wc * p_i), th = tanhf(wh * p_i);
+            const float sech2 = 1.0f - th * th;
+            const float dphi_i = dPhi[i] + (ds * ws * cs - dc * wc * sn + dh * wh * sech2);
+            a.dphi[(long long)i * a.ld + x] = dphi_i * pod[i];
+            om_acc[3 * i] += ds * p_i * cs;
+            om_acc[3 * i + 1] -= dc * p_i * sn;
+            om_acc[3 * i + 2] += dh * p_i * sech2;
+        }
+        {
+            int g = 0;
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+#pragma unroll
+                for (int j = i; j < R; ++j, ++g) gr_acc[g] = fmaf(Phi[i], Phi[j], gr_acc[g]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3 * R; ++i) {
+        const float v = warp_sum(om_acc[i]);
+        if (lane == 0) red_s[warp][i] = (double)v;
+    }
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        const float v = warp_sum(gr_acc[g]);
+        if (lane == 0) red_s[warp][3 * R + g] = (double)v;
+    }
+    __syncthreads();
+    // the slot in the layout reduce_partials_kernel sums: [loss | Phi^T Phi (kMaxR x kMaxR, upper triangle) | d omega]
+    double* out = a.Spart + (long long)(slot_base + blockIdx.x) * kScal;
+    for (int i = tid; i < kScal; i += kCrTile) {
+        int src = -1;
+        if (i >= 1 + kMaxR * kMaxR && i < 1 + kMaxR * kMaxR + 3 * R) src = i - (1 + kMaxR * kMaxR);
+        else if (i >= 1 && i < 1 + kMaxR * kMaxR) {
+            const int gi = (i - 1) / kMaxR, gj = (i - 1) % kMaxR;
+            if (gi < R && gj < R && gj >= gi) src = 3 * R + (gi * R - gi * (gi - 1) / 2 + (gj - gi));
+        }
+        double sum = 0.0;
+        if (src >= 0)
+            for (int w = 0; w < kCrTile / 32; ++w) sum += red_s[w][src];
+        out[i] = sum;
+    }
+}
+template <int R, int P>
+static bool ct_table_matches(const FusedArgs& a) {
+    constexpr int T = CtMono<R, P>::T;
+    if (a.r != R || a.T != T) return false;
+    for (int j = 1; j < T; ++j)
+        if (a.mt.parent[j] != kCtMono<R, P>.parent[j] || a.mt.last[j] != kCtMono<R, P>.last[j] || a.mt.deg[j] != kCtMono<R, P>.deg[j]) return false;
+    return true;
+}
+template <int R, int P>
+static bool chain_rule_reg_try(const FusedArgs& a, int slot_base, int sms, int* nslots, cudaStream_t st, cudaError_t* err) {
+    if (!ct_table_matches<R, P>(a)) return false;
+    const long long ntiles = a.ld / kCrTile;
+    const long long cap = (long long)sms * 4;  // 94 registers at r4p2: four CTAs of 128 threads per SM
+    const int gc = (int)(ntiles < cap ? ntiles : cap);
+    chain_rule_reg_kernel<R, P><<<gc, kCrTile, 0, st>>>(a, slot_base);
+    *err = cudaGetLastError();
+    *nslots = gc;
+    return true;
+}
+// the libraries the fused tcgen05 kernel covers most often (K <= 32): r4p2 (headline), r2p2, r2p3, r2p4, r3p2, r3p3
+static bool chain_rule_reg_dispatch(const FusedArgs& a, int slot_base, int sms, int* nslots, cudaStream_t st, cudaError_t* err) {
+    static const bool off = getenv("DESMO_CHAIN_RULE_GENERIC") != nullptr;  // A/B switch: force the table-driven kernel
+    if (off || a.ld % kCrTile != 0 || slot_base + sms * 4 > kMaxSlots) return false;
+    return chain_rule_reg_try<4, 2>(a, slot_base, sms, nslots, st, err) || chain_rule_reg_try<2, 2>(a, slot_base, sms, nslots, st, err) ||
+           chain_rule_reg_try<2, 3>(a, slot_base, sms, nslots, st, err) || chain_rule_reg_try<2, 4>(a, slot_base, sms, nslots, st, err) ||
+           chain_rule_reg_try<3, 2>(a, slot_base, sms, nslots, st, err) || chain_rule_reg_try<3, 3>(a, slot_base, sms, nslots, st, err);
+}
+
 // chain_rule_kernel<R> for R = a.r (1..kMaxR)
 template <int R>
 static cudaError_t chain_rule_go(const FusedArgs& a, int slot_base, int gc, size_t sm, cudaStream_t st) {
@@ -509,6 +693,19 @@ int chain_rule_launch(const desmo_shape* s, const MonoTable& mt, int T, int Kp, 
     a.n = s->n; a.ld = s->ld; a.m = s->m; a.mld = s->mld; a.r = s->r; a.T = T; a.K = T + 3 * s->r;
     a.scale = (float)(2.0 / ((double)s->n_global * (double)s->m));
     a.mt = mt;
+    {
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
+            DESMO_CUDA(cudaGetDevice(&dev));
+            DESMO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        cudaError_t err = cudaSuccess;
+        if (chain_rule_reg_dispatch(a, slot_base, sms, nslots, st, &err)) {  // compile-time library: registers only
+            DESMO_CUDA(err);
+            return DESMO_OK;
+        }
+    }
     const long long ntiles = (a.ld + kTile - 1) / kTile;
     const int gc = (int)(ntiles < 296 ? ntiles : 296);  // persistent: two CTAs per SM
     DESMO_CUDA(chain_rule_dispatch(a, slot_base, gc, 0, st));

@@ -862,21 +862,58 @@ __global__ void __launch_bounds__(tc::THREADS, 1) fused_tc_kernel(const TcArgs a
 }
 
 // ------------------------------------------------------------------------------------------------- host side
-static cudaEvent_t g_ev[2] = {nullptr, nullptr};
-static bool g_ev_valid = false;
-int fused_event_ms(float* ms) {  // duration of the last dominant-kernel launch (DESMO_KERNEL_EVENTS=1); synchronises
-    if (!g_ev_valid) return DESMO_ERR_ARG;
-    if (cudaEventSynchronize(g_ev[1]) != cudaSuccess) return DESMO_ERR_CUDA;
-    return cudaEventElapsedTime(ms, g_ev[0], g_ev[1]) == cudaSuccess ? DESMO_OK : DESMO_ERR_CUDA;
+// Kernel timing (DESMO_KERNEL_EVENTS=1).  Eager launches record into a ring of event pairs, so that a caller can launch many steps
+// back to back (no host synchronisation in between: a launch after an idle gap runs measurably slower) and read the mean afterwards.
+// Launches inside a stream capture record one extra pair as EXTERNAL event nodes of the graph: after a replay it holds the kernel's
+// duration inside that replay, i.e. inside the caller's timed region.
+constexpr int kEvRing = 64;
+static cudaEvent_t g_ev[kEvRing][2];
+static cudaEvent_t g_cap_ev[2] = {nullptr, nullptr};
+static bool g_ev_made = false, g_cap_recorded = false;
+static long long g_ev_n = 0;  // eager launches recorded since the last reset
+int fused_event_ms(float* ms) {  // duration of the last eager dominant-kernel launch; synchronises
+    if (g_ev_n < 1) return DESMO_ERR_ARG;
+    cudaEvent_t* p = g_ev[(g_ev_n - 1) % kEvRing];
+    if (cudaEventSynchronize(p[1]) != cudaSuccess) return DESMO_ERR_CUDA;
+    return cudaEventElapsedTime(ms, p[0], p[1]) == cudaSuccess ? DESMO_OK : DESMO_ERR_CUDA;
+}
+int fused_event_mean_ms(float* mean_ms, int* launches, int reset) {  // mean over the (at most kEvRing) eager launches since the last reset
+    const long long cnt = g_ev_n < kEvRing ? g_ev_n : kEvRing;
+    double sum = 0.0;
+    for (long long i = g_ev_n - cnt; i < g_ev_n; ++i) {
+        cudaEvent_t* p = g_ev[i % kEvRing];
+        float ms = 0.0f;
+        if (cudaEventSynchronize(p[1]) != cudaSuccess || cudaEventElapsedTime(&ms, p[0], p[1]) != cudaSuccess) return DESMO_ERR_CUDA;
+        sum += ms;
+    }
+    if (mean_ms) *mean_ms = cnt ? (float)(sum / (double)cnt) : 0.0f;
+    if (launches) *launches = (int)cnt;
+    if (reset) g_ev_n = 0;
+    return DESMO_OK;
+}
+int fused_event_graph_ms(float* ms) {  // the dominant kernel inside the last replay of a captured step; synchronises
+    if (!g_cap_recorded) return DESMO_ERR_ARG;
+    if (cudaEventSynchronize(g_cap_ev[1]) != cudaSuccess) return DESMO_ERR_CUDA;
+    return cudaEventElapsedTime(ms, g_cap_ev[0], g_cap_ev[1]) == cudaSuccess ? DESMO_OK : DESMO_ERR_CUDA;
 }
 void fused_event_record(int which, cudaStream_t st) {
     static const bool on = getenv("DESMO_KERNEL_EVENTS") != nullptr;
     if (!on) return;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return;  // never inside a graph capture
-    if (!g_ev[0]) { cudaEventCreate(&g_ev[0]); cudaEventCreate(&g_ev[1]); }
-    cudaEventRecord(g_ev[which], st);
-    if (which == 1) g_ev_valid = true;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) return;
+    if (cap != cudaStreamCaptureStatusNone) {
+        // events are created by the first eager launch (no resource creation inside a capture); without one, the graph is left alone
+        if (g_ev_made && cudaEventRecordWithFlags(g_cap_ev[which], st, cudaEventRecordExternal) == cudaSuccess && which == 1)
+            g_cap_recorded = true;
+        return;
+    }
+    if (!g_ev_made) {
+        for (int i = 0; i < kEvRing; ++i) { cudaEventCreate(&g_ev[i][0]); cudaEventCreate(&g_ev[i][1]); }
+        cudaEventCreate(&g_cap_ev[0]); cudaEventCreate(&g_cap_ev[1]);
+        g_ev_made = true;
+    }
+    if (which == 0) ++g_ev_n;
+    cudaEventRecord(g_ev[(g_ev_n - 1) % kEvRing][which], st);
 }
 
 static unsigned long long* g_dbg_host = nullptr;

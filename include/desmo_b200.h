@@ -152,6 +152,15 @@ int desmo_term_norms(const desmo_shape* s, const float* g2, const float* gates, 
  * desmo_fused_residual_grad call, recorded when DESMO_KERNEL_EVENTS is set in the environment.  Synchronous. */
 int desmo_last_fused_kernel_ms(float* ms);
 
+/* Measurement: mean device time of the dominant kernel over the eager desmo_fused_residual_grad calls since the last reset (the most
+ * recent 64 at most), so that a caller can launch steps back to back without synchronising in between; reset != 0 starts a new
+ * series.  Synchronous. */
+int desmo_fused_kernel_ms_mean(float* mean_ms, int32_t* launches, int32_t reset);
+
+/* Measurement: device time of the dominant kernel inside the last replay of a CUDA graph that captured desmo_fused_residual_grad
+ * (external event-record nodes, added when DESMO_KERNEL_EVENTS is set and one eager call preceded the capture).  Synchronous. */
+int desmo_graph_fused_kernel_ms(float* ms);
+
 /* Diagnostics: per-CTA phase timers (cycles) of the tcgen05 fused kernel, recorded when DESMO_TC_DEBUG is set in the
  * environment; 16 counters per CTA.  Synchronous. */
 int desmo_debug_timers(const desmo_shape* s, void* workspace, uint64_t* out_host, int32_t count);
