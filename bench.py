@@ -407,11 +407,7 @@ def main():
             ev1.record()
             barrier()
             ms_total = ev0.elapsed_time(ev1)
-            sample_graph_kernel()  # the last step of the timed region
-            for _ in range(4):     # and the last step of four more back-to-back bursts (a replay after an idle gap runs slower)
-                for _ in range(4):
-                    trainer.step()
-                sample_graph_kernel()
+            sample_graph_kernel()  # the dominant kernel inside the last step of the timed region
         else:
             ms_total = 0.0
             for _ in range(args.steps):
@@ -423,34 +419,59 @@ def main():
                 ms_total += ev0.elapsed_time(ev1)
                 sample_graph_kernel()
             barrier()
-        # the fused call (dominant kernel + chain rule + partial reduction) and the dominant kernel alone in EAGER launches issued back
-        # to back (no host synchronisation between launches); kernel events are recorded inside the library on the launching stream
-        e.build_w(False)
-        torch.cuda.synchronize()
-        n_eager = max(1, min(args.steps, 64))
-        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_eager)]
+    # The dominant kernel's launch durations over a SECOND timed region of the same K steps, launched eagerly and back to back
+    # (the library brackets the kernel with one CUDA event pair per launch on the launching stream; the events of a captured
+    # step can only keep the last replay).  The region starts from the same state as the first one: synchronised, after a pause
+    # that lets the board's power average decay -- under load the step time drifts upwards as the 1000 W limit is approached,
+    # so a kernel timed in isolated, synchronised launches is not the kernel of the timed region.
+    kms_series, eager_ms_step, clk_b = [], None, None
+    n_eager = max(1, min(args.steps, 64))
+    if have_dom:
+        time.sleep(1.5)
+        trainer.use_cuda_graph = False
+        for _ in range(args.warmup):
+            trainer.step()
+        clk_b = ClockSampler(local_rank)
+        clk_b.__enter__()
+        barrier()
         e.lib.desmo_fused_kernel_ms_mean(None, None, 1)  # start a new series
-        for k0, k1 in pairs:
-            if l2_flush is not None:
-                l2_flush.fill_(1)
-            k0.record()
-            e.fused_residual_grad()
-            k1.record()
-        torch.cuda.synchronize()
-        kms = sum(k0.elapsed_time(k1) for k0, k1 in pairs) / n_eager
-        kms_eager = None
-        if have_dom:
-            dom, cnt = ctypes.c_float(0.0), ctypes.c_int32(0)
-            _lib.check(e.lib.desmo_fused_kernel_ms_mean(ctypes.byref(dom), ctypes.byref(cnt), 1), "desmo_fused_kernel_ms_mean")
-            kms_eager = float(dom.value)
-        if graph_samples:
-            kms_dom, kms_src = sum(graph_samples) / len(graph_samples), (
-                f"CUDA events around the kernel inside the captured step (external event nodes), mean of {len(graph_samples)} replays: "
-                + ("the last step of the timed region and of four further 4-step bursts" if l2_flush is None else "every timed step"))
-        elif kms_eager is not None:
-            kms_dom, kms_src = kms_eager, f"CUDA events around the kernel, {n_eager} eager launches back to back"
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if l2_flush is None:
+            r0.record()
+            for _ in range(n_eager):
+                trainer.step()
+            r1.record()
+            torch.cuda.synchronize()
+            eager_ms_step = r0.elapsed_time(r1) / n_eager
         else:
-            kms_dom, kms_src = kms, "the whole fused call (torch events)"
+            for _ in range(n_eager):
+                l2_flush.fill_(1)
+                trainer.step()
+            torch.cuda.synchronize()
+        clk_b.__exit__(None, None, None)
+        trainer.use_cuda_graph = True
+        buf, cnt = (ctypes.c_float * 64)(), ctypes.c_int32(0)
+        _lib.check(e.lib.desmo_fused_kernel_ms_series(buf, 64, ctypes.byref(cnt)), "desmo_fused_kernel_ms_series")
+        kms_series = [float(buf[i]) for i in range(cnt.value)]
+    # the whole fused call (dominant kernel + chain rule + partial reduction), eager launches back to back, torch events
+    e.build_w(False)
+    torch.cuda.synchronize()
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_eager)]
+    for k0, k1 in pairs:
+        if l2_flush is not None:
+            l2_flush.fill_(1)
+        k0.record()
+        e.fused_residual_grad()
+        k1.record()
+    torch.cuda.synchronize()
+    kms = sum(k0.elapsed_time(k1) for k0, k1 in pairs) / n_eager
+    if kms_series:
+        kms_dom = sum(kms_series) / len(kms_series)
+        kms_src = (f"mean of {len(kms_series)} launches: one CUDA event pair per launch around the kernel on its launching stream, over a "
+                   "second timed region of back-to-back eager steps (region_ms_per_step beside it); kernel_ms_graph_last_step = the same "
+                   "kernel inside the last replay of the first (graph) region")
+    else:
+        kms_dom, kms_src = kms, "the whole fused call (torch events, eager launches back to back)"
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -513,8 +534,11 @@ def main():
         achieved = alg_bytes / (kms_dom * 1e-3) / 1e9
         kernel_name = {1: "fused_fp32_kernel", 2: "fused_tc_kernel", 3: "gemm_planes_kernel x3 per chunk (GEMM path, whole fused call)"}[e.path_used]
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": kernel_name, "kernel_ms": kms_dom, "kernel_ms_source": kms_src, "kernel_ms_eager_back_to_back": kms_eager,
-                "kernel_ms_graph_samples": [round(v, 4) for v in graph_samples], "fused_call_ms": kms, "peak_source": peak_src,
+                "kernel": kernel_name, "kernel_ms": kms_dom, "kernel_ms_source": kms_src,
+                "kernel_ms_series": [round(v, 4) for v in kms_series], "region_ms_per_step": eager_ms_step,
+                "region_clocks": clk_b.summary() if clk_b is not None else None,
+                "kernel_ms_graph_last_step": [round(v, 4) for v in graph_samples][-1:] if l2_flush is None else
+                [round(sum(graph_samples) / max(len(graph_samples), 1), 4)], "fused_call_ms": kms, "peak_source": peak_src,
                 "algorithmic_bytes": alg_bytes}
         if e.path_used == _lib.PATH_GEMM:
             # K > 32: 6 K n m flop on 4 n m bytes -- bound by the tensor pipe; report both roofs, name the binding one

@@ -51,6 +51,7 @@ SIGNATURES: Dict[str, tuple] = {
     "desmo_last_fused_kernel_ms": (C.c_int, [C.POINTER(C.c_float)]),
     "desmo_fused_kernel_ms_mean": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int32]),
     "desmo_graph_fused_kernel_ms": (C.c_int, [C.POINTER(C.c_float)]),
+    "desmo_fused_kernel_ms_series": (C.c_int, [C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32)]),
     "desmo_debug_timers": (C.c_int, [_SP, _vp, _vp, _i32]),
     "desmo_pod_gram": (C.c_int, [_SP] + [_vp] * 4),
     "desmo_pod_eig": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),

@@ -367,6 +367,15 @@ int desmo_fused_kernel_ms_mean(float* mean_ms, int32_t* launches, int32_t reset)
     return rc;
 }
 
+int desmo_fused_kernel_ms_series(float* out_ms, int32_t capacity, int32_t* count) {
+    if (!out_ms || capacity < 1) { set_error("desmo_fused_kernel_ms_series: bad argument"); return DESMO_ERR_ARG; }
+    int n = 0;
+    const int rc = fused_event_series_ms(out_ms, capacity, &n);
+    if (count) *count = n;
+    if (rc) set_error("desmo_fused_kernel_ms_series: CUDA event query failed");
+    return rc;
+}
+
 int desmo_graph_fused_kernel_ms(float* ms) {
     if (!ms) { set_error("desmo_graph_fused_kernel_ms: null"); return DESMO_ERR_ARG; }
     const int rc = fused_event_graph_ms(ms);

@@ -87,6 +87,7 @@ int tc_debug_read(uint64_t* out, int count);
 int fused_event_ms(float* ms);
 int fused_event_mean_ms(float* mean_ms, int* launches, int reset);
 int fused_event_graph_ms(float* ms);
+int fused_event_series_ms(float* out, int capacity, int* count);
 void fused_event_record(int which, cudaStream_t st);
 int launch_update(const UpdateArgs& a, cudaStream_t st);
 int launch_plateau(desmo_plateau* st, const int32_t* step_dev, const float* losses, float* hyper, cudaStream_t stream);

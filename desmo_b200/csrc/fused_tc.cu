@@ -891,6 +891,16 @@ int fused_event_mean_ms(float* mean_ms, int* launches, int reset) {  // mean ove
     if (reset) g_ev_n = 0;
     return DESMO_OK;
 }
+int fused_event_series_ms(float* out, int capacity, int* count) {  // per-launch durations since the last reset, oldest first
+    const long long cnt = g_ev_n < kEvRing ? g_ev_n : kEvRing;
+    int k = 0;
+    for (long long i = g_ev_n - cnt; i < g_ev_n && k < capacity; ++i, ++k) {
+        cudaEvent_t* p = g_ev[i % kEvRing];
+        if (cudaEventSynchronize(p[1]) != cudaSuccess || cudaEventElapsedTime(out + k, p[0], p[1]) != cudaSuccess) return DESMO_ERR_CUDA;
+    }
+    if (count) *count = k;
+    return DESMO_OK;
+}
 int fused_event_graph_ms(float* ms) {  // the dominant kernel inside the last replay of a captured step; synchronises
     if (!g_cap_recorded) return DESMO_ERR_ARG;
     if (cudaEventSynchronize(g_cap_ev[1]) != cudaSuccess) return DESMO_ERR_CUDA;

@@ -156,6 +156,8 @@ int desmo_last_fused_kernel_ms(float* ms);
  * recent 64 at most), so that a caller can launch steps back to back without synchronising in between; reset != 0 starts a new
  * series.  Synchronous. */
 int desmo_fused_kernel_ms_mean(float* mean_ms, int32_t* launches, int32_t reset);
+/* ... and the per-launch durations of that series, oldest first (at most `capacity`, at most 64).  Synchronous. */
+int desmo_fused_kernel_ms_series(float* out_ms, int32_t capacity, int32_t* count);
 
 /* Measurement: device time of the dominant kernel inside the last replay of a CUDA graph that captured desmo_fused_residual_grad
  * (external event-record nodes, added when DESMO_KERNEL_EVENTS is set and one eager call preceded the capture).  Synchronous. */
