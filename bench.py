@@ -369,6 +369,7 @@ def main():
     else:
         sigma = e.pod_from_snapshot()  # POD init on the device (method of snapshots)
         pod_info = dict(e.pod_timing)
+        pod_info["err_pod_rank_r"] = e.pod_error  # POD_analysis' printed rank-r error (CYL:208-211)
         nt = (m + 127) // 128
         pod_info["gram_tflops_fp32_equiv"] = 2.0 * n * m * m / (pod_info["gram_ms"] * 1e-3) / 1e12
         # executed on the tensor pipe as 6 bf16 passes over 128-padded tiles of the upper triangle

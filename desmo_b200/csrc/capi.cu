@@ -359,6 +359,12 @@ int desmo_last_fused_kernel_ms(float* ms) {
     return rc;
 }
 
+int desmo_selftest_tables(void) {
+    const int n = chain_rule_tables_selftest();
+    if (n < 0) set_error("desmo_selftest_tables: a compile-time monomial table differs from build_mono_table");
+    return n;
+}
+
 int desmo_fused_kernel_ms_mean(float* mean_ms, int32_t* launches, int32_t reset) {
     int n = 0;
     const int rc = fused_event_mean_ms(mean_ms, &n, reset);

@@ -554,6 +554,18 @@ static bool chain_rule_reg_try(const FusedArgs& a, int slot_base, int sms, int* 
     *nslots = gc;
     return true;
 }
+template <int R, int P>
+static int ct_table_selfcheck() {  // host only: the compile-time table against the run-time enumeration of capi.cu
+    FusedArgs a{};
+    a.r = R;
+    a.T = build_mono_table(R, P, &a.mt);
+    return ct_table_matches<R, P>(a) ? 1 : 0;
+}
+int chain_rule_tables_selftest() {  // number of compile-time libraries verified, or -1 on a mismatch
+    const int ok = ct_table_selfcheck<4, 2>() + ct_table_selfcheck<2, 2>() + ct_table_selfcheck<2, 3>() + ct_table_selfcheck<2, 4>() +
+                   ct_table_selfcheck<3, 2>() + ct_table_selfcheck<3, 3>();
+    return ok == 6 ? ok : -1;
+}
 // the libraries the fused tcgen05 kernel covers most often (K <= 32): r4p2 (headline), r2p2, r2p3, r2p4, r3p2, r3p3
 static bool chain_rule_reg_dispatch(const FusedArgs& a, int slot_base, int sms, int* nslots, cudaStream_t st, cudaError_t* err) {
     static const bool off = getenv("DESMO_CHAIN_RULE_GENERIC") != nullptr;  // A/B switch: force the table-driven kernel

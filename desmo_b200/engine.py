@@ -374,6 +374,7 @@ class DesmoEngine:
             ev[1].record()
             if self.n_global != self.n and torch.distributed.is_initialized():
                 torch.distributed.all_reduce(Cm, group=self.pg)
+            trace = Cm.diagonal().sum(dtype=torch.float64)  # = sum of all sigma^2 = ||X||_F^2 (the all-reduced Gram's trace)
             check(self.lib.desmo_pod_eig(self.m, self.r, _ptr(Cm), _ptr(V), _ptr(sigma), _ptr(ws), ws.numel(), self._stream()), "desmo_pod_eig")
             ev[2].record()
             check(self.lib.desmo_pod_project(C.byref(self.shape), _ptr(self.U), _ptr(V), _ptr(sigma), _ptr(self.P), self._stream()),
@@ -382,4 +383,10 @@ class DesmoEngine:
         torch.cuda.synchronize(self.device)
         self.pod_timing = {"gram_ms": ev[0].elapsed_time(ev[1]), "eig_ms": ev[1].elapsed_time(ev[2]), "project_ms": ev[2].elapsed_time(ev[3])}
         self.pod_V, self.pod_gram = V, Cm
+        # POD_analysis' diagnostics (CYL:200-211) without forming X_approx: energy_content = S^2 / sum(S^2) of the r leading modes, its
+        # running sum, and err_POD = ||X - X_r|| / ||X|| = sqrt(1 - sum_{i<r} sigma_i^2 / ||X||_F^2) (Eckart-Young)
+        s2 = sigma.double() ** 2
+        self.pod_energy = (s2 / trace).cpu()
+        self.pod_cumulative_energy = torch.cumsum(self.pod_energy, 0)
+        self.pod_error = float(torch.sqrt(torch.clamp(1.0 - s2.sum() / trace, min=0.0)))
         return sigma

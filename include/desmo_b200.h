@@ -148,6 +148,11 @@ int desmo_library_colnorm2(const desmo_shape* s, const float* P, const float* ph
 int desmo_term_norms(const desmo_shape* s, const float* g2, const float* gates, const float* rows, int32_t fourier_quirk,
                      double* norms_out, void* stream);
 
+/* Diagnostics, host only (no GPU needed): the chain-rule kernels specialised for common libraries carry their monomial table
+ * (POOL_DATA's term order, CYL:376-434) as compile-time constants; this compares each of them with the run-time enumeration
+ * desmo_count_terms / the fused kernels use.  Returns the number of tables verified (> 0) or a negative value on a mismatch. */
+int desmo_selftest_tables(void);
+
 /* Measurement: device time (CUDA events on the launching stream) of the dominant kernel of the last
  * desmo_fused_residual_grad call, recorded when DESMO_KERNEL_EVENTS is set in the environment.  Synchronous. */
 int desmo_last_fused_kernel_ms(float* ms);

@@ -32,6 +32,13 @@ def test_library_term_counts_match_reference_facts():
     assert lib.desmo_num_terms(2, 8) < 0 and lib.desmo_num_terms(0, 2) < 0 and lib.desmo_num_terms(65, 1) < 0
 
 
+def test_compile_time_monomial_tables_match_the_runtime_enumeration():
+    """The register-resident chain-rule kernels (fused_fp32.cu: chain_rule_reg_kernel<R, P>) fold POOL_DATA's term order
+    (CYL:376-434) into the instruction stream; every such table must equal the run-time enumeration the other kernels use."""
+    lib = _lib.load()
+    assert lib.desmo_selftest_tables() == 6
+
+
 def test_shape_validation_and_error_strings():
     lib = _lib.load()
     bad = _lib.make_shape(1000, 100, 4, 2, ld=1000)  # pitch not a multiple of 128

@@ -480,6 +480,13 @@ def test_pod_by_method_of_snapshots_matches_svd(path):
         c = abs(float(P[i] @ modes[:, i]))  # |cos| between our mode i and LAPACK's (sign is a convention)
         assert c > 1 - 1e-4, (i, c)
     assert np.allclose(P @ P.T, np.eye(4), atol=1e-4)
+    # POD_analysis' printed diagnostics (CYL:200-211): energy content of the leading modes and the rank-r reconstruction error
+    Xf = X.astype(np.float32).astype(np.float64)
+    U_, S_, Vt_ = np.linalg.svd(Xf, full_matrices=False)
+    err_ref = np.linalg.norm(Xf - U_[:, :4] @ np.diag(S_[:4]) @ Vt_[:4]) / np.linalg.norm(Xf)
+    assert abs(e.pod_error - err_ref) < 1e-3 * err_ref + 1e-5, (e.pod_error, err_ref)
+    assert rel(e.pod_energy.numpy(), (S_ ** 2 / np.sum(S_ ** 2))[:4]) < 1e-4
+    assert rel(e.pod_cumulative_energy.numpy(), np.cumsum(S_ ** 2 / np.sum(S_ ** 2))[:4]) < 1e-4
 
 
 @pytest.mark.parametrize("path", PATHS)
