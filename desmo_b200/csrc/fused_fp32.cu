@@ -443,9 +443,9 @@ __device__ __forceinline__ void static_for(F&& f) {
     static_for_impl(std::make_integer_sequence<int, N>{}, f);
 }
 
-constexpr int kCrTile = 128;  // points per CTA tile == threads (ld is a multiple of 128)
+constexpr int kCrTile = 256;  // points per CTA tile == threads (the engine pads ld to a multiple of 256; other ld: table-driven kernel)
 template <int R, int P>
-__global__ void __launch_bounds__(kCrTile, 4) chain_rule_reg_kernel(const FusedArgs a, int slot_base) {
+__global__ void __launch_bounds__(kCrTile, 2) chain_rule_reg_kernel(const FusedArgs a, int slot_base) {
     constexpr int T = CtMono<R, P>::T, K = T + 3 * R, NG = R * (R + 1) / 2, NS = 3 * R + NG;
     __shared__ double red_s[kCrTile / 32][NS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -547,7 +547,7 @@ template <int R, int P>
 static bool chain_rule_reg_try(const FusedArgs& a, int slot_base, int sms, int* nslots, cudaStream_t st, cudaError_t* err) {
     if (!ct_table_matches<R, P>(a)) return false;
     const long long ntiles = a.ld / kCrTile;
-    const long long cap = (long long)sms * 4;  // 94 registers at r4p2: four CTAs of 128 threads per SM
+    const long long cap = (long long)sms * 2;  // 94 registers at r4p2: two CTAs of 256 threads per SM (few slots: the partial reduction walks them all)
     const int gc = (int)(ntiles < cap ? ntiles : cap);
     chain_rule_reg_kernel<R, P><<<gc, kCrTile, 0, st>>>(a, slot_base);
     *err = cudaGetLastError();
@@ -569,7 +569,7 @@ int chain_rule_tables_selftest() {  // number of compile-time libraries verified
 // the libraries the fused tcgen05 kernel covers most often (K <= 32): r4p2 (headline), r2p2, r2p3, r2p4, r3p2, r3p3
 static bool chain_rule_reg_dispatch(const FusedArgs& a, int slot_base, int sms, int* nslots, cudaStream_t st, cudaError_t* err) {
     static const bool off = getenv("DESMO_CHAIN_RULE_GENERIC") != nullptr;  // A/B switch: force the table-driven kernel
-    if (off || a.ld % kCrTile != 0 || slot_base + sms * 4 > kMaxSlots) return false;
+    if (off || a.ld % kCrTile != 0 || slot_base + sms * 2 > kMaxSlots) return false;
     return chain_rule_reg_try<4, 2>(a, slot_base, sms, nslots, st, err) || chain_rule_reg_try<2, 2>(a, slot_base, sms, nslots, st, err) ||
            chain_rule_reg_try<2, 3>(a, slot_base, sms, nslots, st, err) || chain_rule_reg_try<2, 4>(a, slot_base, sms, nslots, st, err) ||
            chain_rule_reg_try<3, 2>(a, slot_base, sms, nslots, st, err) || chain_rule_reg_try<3, 3>(a, slot_base, sms, nslots, st, err);
