@@ -736,3 +736,43 @@ def test_split_pass_equals_monolithic(path):
     _lib.check(e.lib.desmo_fused_residual_grad_finish(*args), "finish")
     torch.cuda.synchronize()
     assert torch.equal(e.red, want_red) and torch.equal(e.dphi, want_dphi)
+
+
+def test_kernel_event_timing_entry_points():
+    """Measurement entry points (bench.py's roofline): with DESMO_KERNEL_EVENTS set, every eager launch of the dominant kernel is
+    bracketed by its own CUDA event pair (series / mean / last agree), and a captured step carries the pair as external event nodes
+    (the kernel's duration inside the last replay).  The switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+
+    code = r"""
+import ctypes, torch
+from desmo_b200 import DESMO, DesmoTrainer
+m = DESMO(40000, 128, 2, 4, 10.0, device=torch.device('cuda:0'))
+e = m.engine
+e.set_snapshot(torch.randn(128, 40000, device=e.device))
+e.P[:, :40000] = torch.randn(4, 40000, device=e.device) / 200.0
+lib = e.lib
+assert lib.desmo_fused_kernel_ms_mean(None, None, 1) == 0
+for _ in range(5):
+    e.train_step()
+buf, cnt, mean, n = (ctypes.c_float * 64)(), ctypes.c_int32(0), ctypes.c_float(0), ctypes.c_int32(0)
+assert lib.desmo_fused_kernel_ms_series(buf, 64, ctypes.byref(cnt)) == 0 and cnt.value == 5
+last = ctypes.c_float(0)
+assert lib.desmo_last_fused_kernel_ms(ctypes.byref(last)) == 0 and abs(last.value - buf[4]) < 1e-6
+assert lib.desmo_fused_kernel_ms_mean(ctypes.byref(mean), ctypes.byref(n), 1) == 0 and n.value == 5
+vals = [buf[i] for i in range(5)]
+assert all(0.0 < v < 50.0 for v in vals) and abs(mean.value - sum(vals) / 5) < 1e-4
+assert lib.desmo_fused_kernel_ms_mean(ctypes.byref(mean), ctypes.byref(n), 0) == 0 and n.value == 0   # the series was reset
+t = DesmoTrainer(m, use_cuda_graph=True, device_scheduler=True)
+for _ in range(3):
+    t.step()
+g = ctypes.c_float(0)
+assert lib.desmo_graph_fused_kernel_ms(ctypes.byref(g)) == 0 and 0.0 < g.value < 50.0
+assert lib.desmo_fused_kernel_ms_mean(ctypes.byref(mean), ctypes.byref(n), 0) == 0 and n.value == 1    # the trainer's one eager warm-up
+print('OK', vals, g.value)
+"""
+    env = dict(os.environ, DESMO_KERNEL_EVENTS="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
