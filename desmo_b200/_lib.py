@@ -49,6 +49,7 @@ SIGNATURES: Dict[str, tuple] = {
     "desmo_library_colnorm2": (C.c_int, [_SP] + [_vp] * 5),
     "desmo_term_norms": (C.c_int, [_SP, _vp, _vp, _vp, _i32, _vp, _vp]),
     "desmo_selftest_tables": (C.c_int, []),
+    "desmo_selftest_chain_sweep": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "desmo_last_fused_kernel_ms": (C.c_int, [C.POINTER(C.c_float)]),
     "desmo_fused_kernel_ms_mean": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int32]),
     "desmo_graph_fused_kernel_ms": (C.c_int, [C.POINTER(C.c_float)]),

@@ -365,6 +365,15 @@ int desmo_selftest_tables(void) {
     return n;
 }
 
+int desmo_selftest_chain_sweep(int32_t r, int32_t polyorder, const float* d_row, const float* phi_row, float* dphi_out) {
+    if (!d_row || !phi_row || !dphi_out) { set_error("desmo_selftest_chain_sweep: null pointer"); return DESMO_ERR_ARG; }
+    if (chain_rule_sweep_selftest(r, polyorder, d_row, phi_row, dphi_out)) {
+        set_error("desmo_selftest_chain_sweep: no compile-time chain-rule kernel for r=%d polyorder=%d", r, polyorder);
+        return DESMO_ERR_UNSUPPORTED;
+    }
+    return DESMO_OK;
+}
+
 int desmo_fused_kernel_ms_mean(float* mean_ms, int32_t* launches, int32_t reset) {
     int n = 0;
     const int rc = fused_event_mean_ms(mean_ms, &n, reset);

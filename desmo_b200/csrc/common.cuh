@@ -85,6 +85,7 @@ int fused_tc(const desmo_shape* s, const MonoTable& mt, int T, int Kp, const flo
 int fused_tc_supported(const desmo_shape* s, int Kp);
 int tc_debug_read(uint64_t* out, int count);
 int chain_rule_tables_selftest();
+int chain_rule_sweep_selftest(int r, int p, const float* d_row, const float* phi_row, float* dphi_out);
 int fused_event_ms(float* ms);
 int fused_event_mean_ms(float* mean_ms, int* launches, int reset);
 int fused_event_graph_ms(float* ms);

@@ -435,12 +435,37 @@ template <int R, int P>
 inline constexpr CtMono<R, P> kCtMono{};
 
 template <int... Is, class F>
-__device__ __forceinline__ void static_for_impl(std::integer_sequence<int, Is...>, F&& f) {
+__host__ __device__ __forceinline__ void static_for_impl(std::integer_sequence<int, Is...>, F&& f) {
     (f(std::integral_constant<int, Is>{}), ...);
 }
 template <int N, class F>
-__device__ __forceinline__ void static_for(F&& f) {
+__host__ __device__ __forceinline__ void static_for(F&& f) {
     static_for_impl(std::make_integer_sequence<int, N>{}, f);
+}
+
+// Monomial part of the chain rule for ONE point, fully unrolled over the compile-time table: forward L_j = L_parent(j) * Phi_last(j)
+// (POOL_DATA's left-to-right products, CYL:390-431), then the reverse sweep  dPhi_last += adj_j * L_parent,  adj_parent += adj_j * Phi_last.
+// A[0..T) holds the adjoints dL/dG_j on entry and is clobbered.  Host-callable so that the CPU suite can check the unrolled code
+// against the oracle (desmo_selftest_chain_sweep); on the device everything is registers.
+template <int R, int P, int NA>
+__host__ __device__ __forceinline__ void chain_sweep_ct(float (&A)[NA], const float (&Phi)[R], float (&dPhi)[R]) {
+    constexpr int T = CtMono<R, P>::T;
+    static_assert(NA >= T, "adjoint array shorter than the library");
+    float L[T];
+    L[0] = 1.0f;
+    static_for<T - 1>([&](auto jc) {
+        constexpr int j = decltype(jc)::value + 1;
+        constexpr int par = kCtMono<R, P>.parent[j], v = kCtMono<R, P>.last[j], dg = kCtMono<R, P>.deg[j];
+        if constexpr (dg == 1) L[j] = Phi[v];
+        else L[j] = L[par] * Phi[v];
+    });
+    static_for<T - 1>([&](auto jc) {
+        constexpr int j = T - 1 - decltype(jc)::value;
+        constexpr int par = kCtMono<R, P>.parent[j], v = kCtMono<R, P>.last[j];
+        const float adj = A[j];
+        dPhi[v] = fmaf(adj, L[par], dPhi[v]);
+        if constexpr (par > 0) A[par] = fmaf(adj, Phi[v], A[par]);
+    });
 }
 
 constexpr int kCrTile = 256;  // points per CTA tile == threads (the engine pads ld to a multiple of 256; other ld: table-driven kernel)
@@ -466,7 +491,7 @@ __global__ void __launch_bounds__(kCrTile, 2) chain_rule_reg_kernel(const FusedA
             ph[i] = __ldg(a.phi + (long long)i * a.ld + x);
             pod[i] = __ldg(a.P + (long long)i * a.ld + x);
         }
-        float Phi[R], dPhi[R], L[T];
+        float Phi[R], dPhi[R];
 #pragma unroll
         for (int i = 0; i < R; ++i) {
             Phi[i] = ph[i] * pod[i];
@@ -474,20 +499,7 @@ __global__ void __launch_bounds__(kCrTile, 2) chain_rule_reg_kernel(const FusedA
         }
 #pragma unroll
         for (int j = 0; j < K; ++j) A[j] = xin ? A[j] * a.scale : 0.0f;
-        L[0] = 1.0f;
-        static_for<T - 1>([&](auto jc) {
-            constexpr int j = decltype(jc)::value + 1;
-            constexpr int par = kCtMono<R, P>.parent[j], v = kCtMono<R, P>.last[j], dg = kCtMono<R, P>.deg[j];
-            if constexpr (dg == 1) L[j] = Phi[v];
-            else L[j] = L[par] * Phi[v];
-        });
-        static_for<T - 1>([&](auto jc) {
-            constexpr int j = T - 1 - decltype(jc)::value;
-            constexpr int par = kCtMono<R, P>.parent[j], v = kCtMono<R, P>.last[j];
-            const float adj = A[j];
-            dPhi[v] = fmaf(adj, L[par], dPhi[v]);
-            if constexpr (par > 0) A[par] = fmaf(adj, Phi[v], A[par]);
-        });
+        chain_sweep_ct<R, P>(A, Phi, dPhi);
 #pragma unroll
         for (int i = 0; i < R; ++i) {
             const float p_i = Phi[i];
@@ -565,6 +577,23 @@ int chain_rule_tables_selftest() {  // number of compile-time libraries verified
     const int ok = ct_table_selfcheck<4, 2>() + ct_table_selfcheck<2, 2>() + ct_table_selfcheck<2, 3>() + ct_table_selfcheck<2, 4>() +
                    ct_table_selfcheck<3, 2>() + ct_table_selfcheck<3, 3>();
     return ok == 6 ? ok : -1;
+}
+template <int R, int P>
+static bool chain_sweep_host_try(int r, int p, const float* d_row, const float* phi_row, float* dphi_out) {
+    if (r != R || p != P) return false;
+    constexpr int T = CtMono<R, P>::T;
+    float A[T], Phi[R], dPhi[R];
+    for (int j = 0; j < T; ++j) A[j] = d_row[j];
+    for (int i = 0; i < R; ++i) { Phi[i] = phi_row[i]; dPhi[i] = 0.0f; }
+    chain_sweep_ct<R, P>(A, Phi, dPhi);
+    for (int i = 0; i < R; ++i) dphi_out[i] = dPhi[i];
+    return true;
+}
+// host only: the unrolled sweep of the specialised kernels applied to one point; 0 when (r, p) has a compile-time kernel
+int chain_rule_sweep_selftest(int r, int p, const float* d_row, const float* phi_row, float* dphi_out) {
+    return (chain_sweep_host_try<4, 2>(r, p, d_row, phi_row, dphi_out) || chain_sweep_host_try<2, 2>(r, p, d_row, phi_row, dphi_out) ||
+            chain_sweep_host_try<2, 3>(r, p, d_row, phi_row, dphi_out) || chain_sweep_host_try<2, 4>(r, p, d_row, phi_row, dphi_out) ||
+            chain_sweep_host_try<3, 2>(r, p, d_row, phi_row, dphi_out) || chain_sweep_host_try<3, 3>(r, p, d_row, phi_row, dphi_out)) ? 0 : 1;
 }
 // the libraries the fused tcgen05 kernel covers most often (K <= 32): r4p2 (headline), r2p2, r2p3, r2p4, r3p2, r3p3
 static bool chain_rule_reg_dispatch(const FusedArgs& a, int slot_base, int sms, int* nslots, cudaStream_t st, cudaError_t* err) {

@@ -152,6 +152,9 @@ int desmo_term_norms(const desmo_shape* s, const float* g2, const float* gates, 
  * (POOL_DATA's term order, CYL:376-434) as compile-time constants; this compares each of them with the run-time enumeration
  * desmo_count_terms / the fused kernels use.  Returns the number of tables verified (> 0) or a negative value on a mismatch. */
 int desmo_selftest_tables(void);
+/* ... and applies the unrolled reverse sweep of such a kernel to ONE point on the host: d_row[T] = dL/dG over the monomial columns,
+ * phi_row[r] = Phi(x); dphi_out[r] = sum_j d_row[j] * dG_j/dPhi_i.  DESMO_ERR_UNSUPPORTED when (r, polyorder) has no specialised kernel. */
+int desmo_selftest_chain_sweep(int32_t r, int32_t polyorder, const float* d_row, const float* phi_row, float* dphi_out);
 
 /* Measurement: device time (CUDA events on the launching stream) of the dominant kernel of the last
  * desmo_fused_residual_grad call, recorded when DESMO_KERNEL_EVENTS is set in the environment.  Synchronous. */

@@ -39,6 +39,33 @@ def test_compile_time_monomial_tables_match_the_runtime_enumeration():
     assert lib.desmo_selftest_tables() == 6
 
 
+@pytest.mark.parametrize("r,p", [(4, 2), (2, 2), (2, 3), (2, 4), (3, 2), (3, 3)])
+def test_unrolled_chain_rule_sweep_matches_the_library_derivative(r, p):
+    """The reverse sweep the specialised chain-rule kernels run per point (chain_sweep_ct, the same inlined code on host and device)
+    against d/dPhi of POOL_DATA's monomials (CYL:376-434) in float64: dPhi_i = sum_j D_j * d(prod_q Phi_idx_j[q]) / dPhi_i."""
+    import itertools
+
+    lib = _lib.load()
+    combos = [()] + [c for d in range(1, p + 1) for c in itertools.combinations_with_replacement(range(r), d)]
+    T = len(combos)
+    assert T == orc.number_of_terms(r, p)
+    rng = np.random.default_rng(r * 10 + p)
+    for _ in range(20):
+        D = rng.standard_normal(T).astype(np.float32)
+        Phi = (rng.standard_normal(r) * 1.5).astype(np.float32)
+        want = np.zeros(r)
+        for j, c in enumerate(combos):
+            for i in set(c):
+                k = c.count(i)
+                rest = np.prod([float(Phi[q]) for q in c if q != i]) if any(q != i for q in c) else 1.0
+                want[i] += float(D[j]) * k * float(Phi[i]) ** (k - 1) * rest
+        got = np.zeros(r, np.float32)
+        fp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))  # noqa: E731
+        assert lib.desmo_selftest_chain_sweep(r, p, fp(D), fp(Phi), fp(got)) == 0
+        assert np.allclose(got, want, rtol=2e-5, atol=2e-5 * np.abs(want).max()), (got, want)
+    assert lib.desmo_selftest_chain_sweep(5, 2, fp(D), fp(Phi), fp(got)) != 0  # no specialised kernel: reported, not guessed
+
+
 def test_shape_validation_and_error_strings():
     lib = _lib.load()
     bad = _lib.make_shape(1000, 100, 4, 2, ld=1000)  # pitch not a multiple of 128
