@@ -420,7 +420,7 @@ def main():
                 ms_total += ev0.elapsed_time(ev1)
                 sample_graph_kernel()
             barrier()
-    # The dominant kernel's launch durations over a SECOND timed region of the same K steps, launched eagerly and back to back
+    # The dominant kernel's launch durations over a SECOND timed region of the same K steps (the 64 most recent at most), launched eagerly and back to back
     # (the library brackets the kernel with one CUDA event pair per launch on the launching stream; the events of a captured
     # step can only keep the last replay).  The region starts from the same state as the first one: synchronised, after a pause
     # that lets the board's power average decay -- under load the step time drifts upwards as the 1000 W limit is approached,
