@@ -198,7 +198,9 @@ def count_graph_kernels(torch, engine):
         from cuda.bindings import runtime as rt
 
         state = {k: getattr(engine, k).clone() for k in ("phi", "phi_m", "phi_u", "gates", "gates_m", "gates_u", "rows", "rows_m", "rows_u",
-                                                         "omega", "omega_m", "omega_u", "step_dev")}
+                                                         "omega", "omega_m", "omega_u", "step_dev", "hyper")}
+        if engine.plateau_state is not None:  # the device scheduler's state: its kernel is one of the step's launches
+            state["plateau_state"] = engine.plateau_state.clone()
         side = torch.cuda.Stream(device=engine.device)  # one eager step first: function attributes, NCCL communicator
         side.wait_stream(torch.cuda.current_stream(engine.device))
         with torch.cuda.stream(side):
@@ -377,9 +379,9 @@ def main():
     torch.cuda.synchronize()
     if world > 1 and args.allreduce == "peer":
         e.enable_peer_allreduce()  # collective; falls back to NCCL (peer_status says why) when peer-mapped memory is unavailable
-    launches_per_step, launches_src = count_graph_kernels(torch, e)
     trainer = DesmoTrainer(model, beta=beta, patience=patience, sched_every=sched_every, use_cuda_graph=True,
                            device_scheduler=not args.host_scheduler)
+    launches_per_step, launches_src = count_graph_kernels(torch, e)  # after the trainer: its device scheduler is part of the step
 
     def barrier():
         if world > 1:
